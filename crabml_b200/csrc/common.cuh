@@ -1,0 +1,203 @@
+// common.cuh -- internal declarations shared by the CUDA translation units of libcrabml_cuda.
+// B200 (sm_100a) only.  No CPU fallback anywhere in this library.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/crabml_cuda.h"
+
+#define QK_K 256
+
+// ------------------------------------------------------------------------------------------
+// Device-side storage layouts (DESIGN.md "Data layout in HBM").  GGUF stores a weight matrix
+// as rows of AoS blocks whose size is only 2-byte aligned (34 / 18 / 22 / 210 ... bytes).
+// from_cpu repacks each matrix ONCE into planes so that every hot-loop load is a 16-byte,
+// fully coalesced LDG.128; total bytes are unchanged (the f16 scales move to their own plane).
+//
+//   type   plane0                         plane1                 plane2            plane3
+//   Q8_0   qs  int8  [rows][k]            d   f16 [rows][k/32]
+//   Q4_0   qs  u8    [rows][k/32][16]     d   f16 [rows][k/32]
+//   Q4_1   qs  u8    [rows][k/32][16]     d,m f16x2
+//   Q5_0   qs  u8    [rows][k/32][16]     d   f16                qh u32 [rows][k/32]
+//   Q5_1   qs  u8    [rows][k/32][16]     d,m f16x2              qh u32
+//   Q2_K   qs  u8    [rows][k/256][64]    scales u8 [..][16]     d,dmin f16x2
+//   Q3_K   qs  u8    [rows][k/256][64]    hmask u8 [..][32]      scales u8 [..][12]   d f16
+//   Q4_K   AoS 144 B blocks (already 16 B aligned: 16 B header + 128 B qs)
+//   Q5_K   AoS 176 B blocks (16 B header + 32 B qh + 128 B qs)
+//   Q6_K   ql  u8    [rows][k/256][128]   qh u8 [..][64]         scales i8 [..][16]   d f16
+//   Q8_K   qs  int8  [rows][k]            d   f32 [rows][k/256]
+// ------------------------------------------------------------------------------------------
+#define CC_MAX_PLANES 4
+
+struct cc_device;
+
+struct cc_buf {
+    cc_device* dev = nullptr;
+    std::atomic<int> refs{1};
+    int32_t dtype = CC_F32;
+    int64_t nelems = 0;        // capacity in elements
+    void* base = nullptr;      // allocation base (plane[0] for quantized types)
+    size_t bytes = 0;          // allocation size
+    bool pooled = false;       // came from the activation pool (size class = bytes)
+    int64_t rows = 0, cols = 0;  // quantized matrices
+    uint8_t* plane[CC_MAX_PLANES] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// On-device activation formats: what buf/api.rs:195-228 `quantize` produces, as SoA.
+struct ActQ8_0 {          // partner of Q8_0 / Q4_0 / Q5_0 (buf_q8_0.rs:87-134)
+    int8_t* qs;           // [b][k]
+    float* d;             // [b][k/32]   = f32(f16(d))
+    int32_t* isum;        // [b][k/32]   sum of the block's quants (for the -8 / -16 offsets)
+};
+struct ActQ8_1 {          // partner of Q4_1 / Q5_1 (buf_q8_1.rs:90-129)
+    int8_t* qs;           // [b][k]
+    __half2* ds;          // [b][k/32]   (d, s) as stored f16 values
+};
+struct ActQ8_K {          // partner of all K-quants (buf_q8_k.rs:84-131)
+    int8_t* qs;           // [b][k]
+    float* d;             // [b][k/256]
+    int16_t* bsums;       // [b][k/16]
+};
+
+struct cc_device {
+    int ordinal = 0;
+    cudaStream_t stream = nullptr;
+    bool debug_named_tensors = false;
+    bool lazy = false;
+    std::string last_error;
+    uint64_t launches = 0;
+    int sm_count = 148;
+
+    // f16 LUTs (cpu_device.rs:108-124), computed on the host with libm and uploaded
+    uint16_t* exp_lut = nullptr;
+    uint16_t* gelu_lut = nullptr;
+
+    // activation scratch for matmul_vec (grown on demand; stream-ordered reuse)
+    void* act_scratch = nullptr;
+    size_t act_scratch_bytes = 0;
+
+    // stream-ordered size-class pool for activations
+    std::mutex mu;
+    std::unordered_map<size_t, std::vector<void*>> free_lists;
+    size_t pool_live_bytes = 0;
+
+    // pinned staging for export / row indices
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    void* dev_idx = nullptr;      // device copy of row indices
+    size_t dev_idx_bytes = 0;
+
+    // debug tap
+    std::map<std::string, std::vector<float>> debug_tensors;
+};
+
+// ---- error plumbing ------------------------------------------------------------------------
+int cc_fail(cc_device* dev, int code, const char* fmt, ...);
+#define CC_CUDA(dev, call)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return cc_fail((dev), CC_ERR_CUDA, "%s failed: %s (%s:%d)", #call,              \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+    } while (0)
+#define CC_REQUIRE(dev, cond, ...)                                                          \
+    do {                                                                                    \
+        if (!(cond)) return cc_fail((dev), CC_ERR_TENSOR, __VA_ARGS__);                     \
+    } while (0)
+#define CC_LAUNCH_CHECK(dev)                                                                \
+    do {                                                                                    \
+        (dev)->launches++;                                                                  \
+        cudaError_t _e = cudaPeekAtLastError();                                             \
+        if (_e != cudaSuccess)                                                              \
+            return cc_fail((dev), CC_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+    } while (0)
+
+// ---- type facts ------------------------------------------------------------------------------
+int cc_block_elems(int t);
+size_t cc_block_bytes(int t);          // GGUF block size
+int cc_partner_type(int t);            // buf/api.rs:142-159
+bool cc_is_quant(int t);
+
+// ---- device.cu ---------------------------------------------------------------------------------
+int cc_pool_alloc(cc_device* dev, size_t bytes, void** out, size_t* cls);
+void cc_pool_free(cc_device* dev, void* p, size_t cls);
+int cc_new_activation(cc_device* dev, int64_t nelems, int dtype, bool zero, cc_buf** out);
+int cc_ensure_act_scratch(cc_device* dev, size_t bytes);
+int cc_ensure_pinned(cc_device* dev, size_t bytes);
+int cc_ensure_dev_idx(cc_device* dev, size_t bytes);
+
+// ---- repack.cu -----------------------------------------------------------------------------------
+size_t cc_device_layout_bytes(int t, int64_t rows, int64_t cols);
+void cc_assign_planes(cc_buf* b);
+int cc_launch_repack(cc_device* dev, const uint8_t* gguf_dev, cc_buf* dst);           // GGUF AoS -> planes
+int cc_launch_unrepack(cc_device* dev, const cc_buf* src, uint8_t* gguf_dev);          // planes -> GGUF AoS
+int cc_launch_dequant_rows(cc_device* dev, const cc_buf* src, const int64_t* rows_dev, int n_rows,
+                           int64_t cols, void* dst, int dst_dtype);                    // copy_rows_from
+int cc_launch_synth(cc_device* dev, uint8_t* gguf_dev, int t, int64_t nblocks, uint64_t seed, uint64_t tid, float scale);
+
+// ---- quantize.cu ---------------------------------------------------------------------------------
+size_t cc_act_bytes(int act_type, int64_t n);
+ActQ8_0 cc_act_q8_0(void* scratch, int64_t n);
+ActQ8_1 cc_act_q8_1(void* scratch, int64_t n);
+ActQ8_K cc_act_q8_k(void* scratch, int64_t n);
+int cc_launch_quantize(cc_device* dev, const float* x, int64_t n, int act_type, void* scratch);
+int cc_launch_act_to_blocks(cc_device* dev, const void* scratch, int64_t n, int act_type, uint8_t* blocks_dev);
+
+// ---- matvec.cu -----------------------------------------------------------------------------------
+int cc_launch_matvec(cc_device* dev, const cc_buf* w, const void* act_scratch, const float* x_f32,
+                     float* out, int64_t m, int64_t k, int64_t b);
+
+// ---- ops.cu --------------------------------------------------------------------------------------
+int cc_launch_rms_norm(cc_device* dev, float* x, int64_t rows, int64_t cols, float eps);
+int cc_launch_rope(cc_device* dev, float* x, int64_t n_batch, int64_t batch_stride, int64_t head_dim,
+                   int mode, int64_t pos, int64_t rope_dim);
+int cc_launch_softmax(cc_device* dev, float* x, int64_t rows, int64_t cols);
+int cc_launch_silu(cc_device* dev, float* x, int64_t n);
+int cc_launch_gelu(cc_device* dev, float* x, int64_t n);
+int cc_launch_binary(cc_device* dev, float* x, int64_t n, const float* y, int64_t ny, int op);   // 0 add, 1 mul
+int cc_launch_scale(cc_device* dev, float* x, int64_t n, float s);
+int cc_launch_strided_copy(cc_device* dev, const void* src, int src_dtype, const int64_t* sshape,
+                           const int64_t* sstrides, void* dst, int dst_dtype, const int64_t* dstrides,
+                           int64_t dst_offset, int ndim);
+int cc_launch_batch_matmul(cc_device* dev, const float* a, const void* b, int b_dtype, float* c,
+                           int64_t a_batch, int64_t b_batch, int64_t m, int64_t k, int64_t n,
+                           int64_t sb0, int64_t sb1, int64_t sb2);
+
+// ---- small device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// streaming 128-bit load of weight data: read exactly once per token, keep it out of L1
+__device__ __forceinline__ int4 ld_stream_16(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float h2f_bits(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+__device__ __forceinline__ uint16_t f2h_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+#endif

@@ -1,0 +1,303 @@
+// device.cu -- device object, stream, activation pool, buffers, LUT upload.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static std::string g_create_error;
+
+int cc_fail(cc_device* dev, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (dev) dev->last_error = buf; else g_create_error = buf;
+    return code;
+}
+
+// ---- type facts (crabml-core/src/gguf.rs:86-108; block sizes SURVEY Appendix A) ------------------
+int cc_block_elems(int t) {
+    switch (t) {
+    case CC_F32: case CC_F16: return 1;
+    case CC_Q4_0: case CC_Q4_1: case CC_Q5_0: case CC_Q5_1: case CC_Q8_0: case CC_Q8_1: return 32;
+    case CC_Q2_K: case CC_Q3_K: case CC_Q4_K: case CC_Q5_K: case CC_Q6_K: case CC_Q8_K: return 256;
+    }
+    return 0;
+}
+size_t cc_block_bytes(int t) {
+    switch (t) {
+    case CC_F32: return 4; case CC_F16: return 2;
+    case CC_Q4_0: return 18; case CC_Q4_1: return 20; case CC_Q5_0: return 22; case CC_Q5_1: return 24;
+    case CC_Q8_0: return 34; case CC_Q8_1: return 36;
+    case CC_Q2_K: return 84; case CC_Q3_K: return 110; case CC_Q4_K: return 144; case CC_Q5_K: return 176;
+    case CC_Q6_K: return 210; case CC_Q8_K: return 292;
+    }
+    return 0;
+}
+int cc_partner_type(int t) {   // buf/api.rs:142-159
+    switch (t) {
+    case CC_F32: return CC_F32; case CC_F16: return CC_F16;
+    case CC_Q8_0: case CC_Q4_0: case CC_Q5_0: return CC_Q8_0;
+    case CC_Q8_1: case CC_Q4_1: case CC_Q5_1: return CC_Q8_1;
+    case CC_Q2_K: case CC_Q3_K: case CC_Q4_K: case CC_Q5_K: case CC_Q6_K: case CC_Q8_K: return CC_Q8_K;
+    }
+    return -1;
+}
+bool cc_is_quant(int t) { return cc_block_elems(t) > 1; }
+
+// ---- LUTs (cpu_device.rs:108-124): computed with the HOST libm, exactly as the reference does ---
+static float h2f_host(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+static uint16_t f2h_host(float f) { return __half_as_ushort(__float2half_rn(f)); }
+static float gelu_single(float x) {   // gelu.rs:17-21
+    const float COEF_A = 0.044715f;
+    const float SQRT_2_OVER_PI = (float)0.7978845608028654;
+    return 0.5f * x * (1.0f + tanhf(SQRT_2_OVER_PI * x * (1.0f + COEF_A * x * x)));
+}
+
+extern "C" CC_API int cc_device_create(const cc_device_options* opts, cc_device** out) {
+    if (!out) return cc_fail(nullptr, CC_ERR_ARG, "cc_device_create: out is NULL");
+    *out = nullptr;
+    int ord = opts ? opts->device_ordinal : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return cc_fail(nullptr, CC_ERR_CUDA, "no CUDA device available (%s); crabml-cuda has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (ord < 0 || ord >= count) return cc_fail(nullptr, CC_ERR_ARG, "device ordinal %d out of range (%d devices)", ord, count);
+    cc_device* dev = new cc_device();
+    dev->ordinal = ord;
+    dev->debug_named_tensors = opts && opts->debug_named_tensors;
+    dev->lazy = opts && opts->lazy;
+#define CREATE_CUDA(call)                                                                          \
+    do { cudaError_t _e = (call); if (_e != cudaSuccess) { cc_fail(nullptr, CC_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); delete dev; return CC_ERR_CUDA; } } while (0)
+    CREATE_CUDA(cudaSetDevice(ord));
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, ord));
+    dev->sm_count = prop.multiProcessorCount;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+    std::vector<uint16_t> lut(65536);
+    for (uint32_t x = 0; x < 65536; x++) lut[x] = f2h_host(expf(h2f_host((uint16_t)x)));
+    CREATE_CUDA(cudaMalloc(&dev->exp_lut, 65536 * 2));
+    CREATE_CUDA(cudaMemcpy(dev->exp_lut, lut.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    for (uint32_t x = 0; x < 65536; x++) lut[x] = f2h_host(gelu_single(h2f_host((uint16_t)x)));
+    CREATE_CUDA(cudaMalloc(&dev->gelu_lut, 65536 * 2));
+    CREATE_CUDA(cudaMemcpy(dev->gelu_lut, lut.data(), 65536 * 2, cudaMemcpyHostToDevice));
+#undef CREATE_CUDA
+    *out = dev;
+    return CC_OK;
+}
+
+extern "C" CC_API void cc_device_destroy(cc_device* dev) {
+    if (!dev) return;
+    cudaSetDevice(dev->ordinal);
+    cudaStreamSynchronize(dev->stream);
+    for (auto& kv : dev->free_lists)
+        for (void* p : kv.second) cudaFree(p);
+    if (dev->act_scratch) cudaFree(dev->act_scratch);
+    if (dev->pinned) cudaFreeHost(dev->pinned);
+    if (dev->dev_idx) cudaFree(dev->dev_idx);
+    cudaFree(dev->exp_lut);
+    cudaFree(dev->gelu_lut);
+    cudaStreamDestroy(dev->stream);
+    delete dev;
+}
+
+extern "C" CC_API const char* cc_last_error(cc_device* dev) { return dev ? dev->last_error.c_str() : g_create_error.c_str(); }
+extern "C" CC_API uint64_t cc_device_launch_count(cc_device* dev) { return dev ? dev->launches : 0; }
+extern "C" CC_API void* cc_device_stream(cc_device* dev) { return dev ? (void*)dev->stream : nullptr; }
+
+extern "C" CC_API int cc_device_synchronize(cc_device* dev) {
+    if (!dev) return CC_ERR_ARG;
+    CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
+    return CC_OK;
+}
+
+// ---- activation pool: power-of-two size classes, stream-ordered reuse (single stream) -------------
+static size_t size_class(size_t bytes) {
+    size_t c = 512;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+int cc_pool_alloc(cc_device* dev, size_t bytes, void** out, size_t* cls) {
+    size_t c = size_class(bytes ? bytes : 1);
+    *cls = c;
+    {
+        std::lock_guard<std::mutex> g(dev->mu);
+        auto& fl = dev->free_lists[c];
+        if (!fl.empty()) {
+            *out = fl.back();
+            fl.pop_back();
+            return CC_OK;
+        }
+    }
+    CC_CUDA(dev, cudaMalloc(out, c));
+    dev->pool_live_bytes += c;
+    return CC_OK;
+}
+void cc_pool_free(cc_device* dev, void* p, size_t cls) {
+    std::lock_guard<std::mutex> g(dev->mu);
+    dev->free_lists[cls].push_back(p);   // LIFO: deterministic pointer reuse for identical op sequences
+}
+
+int cc_new_activation(cc_device* dev, int64_t nelems, int dtype, bool zero, cc_buf** out) {
+    size_t esz = dtype == CC_F32 ? 4 : 2;
+    void* p = nullptr;
+    size_t cls = 0;
+    int rc = cc_pool_alloc(dev, (size_t)nelems * esz, &p, &cls);
+    if (rc) return rc;
+    if (zero && nelems > 0) CC_CUDA(dev, cudaMemsetAsync(p, 0, (size_t)nelems * esz, dev->stream));
+    cc_buf* b = new cc_buf();
+    b->dev = dev; b->dtype = dtype; b->nelems = nelems; b->base = p; b->bytes = cls; b->pooled = true;
+    b->plane[0] = (uint8_t*)p;
+    *out = b;
+    return CC_OK;
+}
+
+int cc_ensure_act_scratch(cc_device* dev, size_t bytes) {
+    if (bytes <= dev->act_scratch_bytes) return CC_OK;
+    if (dev->act_scratch) {
+        CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
+        CC_CUDA(dev, cudaFree(dev->act_scratch));
+    }
+    size_t nb = size_class(bytes);
+    CC_CUDA(dev, cudaMalloc(&dev->act_scratch, nb));
+    dev->act_scratch_bytes = nb;
+    return CC_OK;
+}
+int cc_ensure_pinned(cc_device* dev, size_t bytes) {
+    if (bytes <= dev->pinned_bytes) return CC_OK;
+    if (dev->pinned) { CC_CUDA(dev, cudaStreamSynchronize(dev->stream)); CC_CUDA(dev, cudaFreeHost(dev->pinned)); }
+    size_t nb = size_class(bytes);
+    CC_CUDA(dev, cudaMallocHost(&dev->pinned, nb));
+    dev->pinned_bytes = nb;
+    return CC_OK;
+}
+int cc_ensure_dev_idx(cc_device* dev, size_t bytes) {
+    if (bytes <= dev->dev_idx_bytes) return CC_OK;
+    if (dev->dev_idx) { CC_CUDA(dev, cudaStreamSynchronize(dev->stream)); CC_CUDA(dev, cudaFree(dev->dev_idx)); }
+    size_t nb = size_class(bytes);
+    CC_CUDA(dev, cudaMalloc(&dev->dev_idx, nb));
+    dev->dev_idx_bytes = nb;
+    return CC_OK;
+}
+
+// ---- buffers -----------------------------------------------------------------------------------------
+extern "C" CC_API void cc_tensor_retain(cc_buf* b) { if (b) b->refs.fetch_add(1); }
+extern "C" CC_API void cc_tensor_release(cc_buf* b) {
+    if (!b) return;
+    if (b->refs.fetch_sub(1) != 1) return;
+    if (b->pooled) cc_pool_free(b->dev, b->base, b->bytes);
+    else if (b->base) { cudaSetDevice(b->dev->ordinal); cudaFree(b->base); }
+    delete b;
+}
+extern "C" CC_API int32_t cc_tensor_dtype(const cc_buf* b) { return b ? b->dtype : -1; }
+extern "C" CC_API int64_t cc_tensor_capacity(const cc_buf* b) { return b ? b->nelems : 0; }
+
+static int64_t prod(const int64_t* shape, int ndim) {
+    int64_t n = 1;
+    for (int i = 0; i < ndim; i++) n *= shape[i];
+    return n;
+}
+
+extern "C" CC_API int cc_tensor_alloc(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t t, cc_buf** out) {
+    if (!dev || !shape || !out || ndim < 1 || ndim > CC_MAX_DIMS) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_alloc: bad argument");
+    CC_REQUIRE(dev, t == CC_F32 || t == CC_F16, "only f32/f16 is supported");   // cpu_tensor.rs:139-141
+    // F32 is zero-filled (vec![0.0; n]); F16 is uninitialised in the reference (buf_f16.rs:23-28), zeroed here
+    return cc_new_activation(dev, prod(shape, ndim), t, true, out);
+}
+
+extern "C" CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size_t nbytes, const int64_t* shape,
+                                  int32_t ndim, int32_t t, cc_buf** out) {
+    if (!dev || !bytes || !shape || !out || ndim < 1 || ndim > CC_MAX_DIMS) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_from_cpu: bad argument");
+    int be = cc_block_elems(t);
+    CC_REQUIRE(dev, be > 0, "from_cpu: unsupported ggml type %d", t);
+    int64_t n = prod(shape, ndim);
+    int64_t cols = shape[ndim - 1], rows = n / (cols ? cols : 1);
+    CC_REQUIRE(dev, cols % be == 0, "from_cpu: last dim %lld is not a multiple of the %d-element block", (long long)cols, be);
+    size_t need = (size_t)(n / be) * cc_block_bytes(t);   // size from shape, not slice length (B16, gguf.rs:742-747)
+    CC_REQUIRE(dev, nbytes >= need, "from_cpu: %zu bytes given, %zu needed for shape", nbytes, need);
+    cc_buf* b = new cc_buf();
+    b->dev = dev; b->dtype = t; b->nelems = n; b->rows = rows; b->cols = cols;
+    if (!cc_is_quant(t)) {
+        b->bytes = need;
+        cudaError_t e = cudaMalloc(&b->base, need ? need : 1);
+        if (e != cudaSuccess) { delete b; return cc_fail(dev, CC_ERR_CUDA, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); }
+        b->plane[0] = (uint8_t*)b->base;
+        e = cudaMemcpyAsync(b->base, bytes, need, cudaMemcpyHostToDevice, dev->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
+        if (e != cudaSuccess) { cudaFree(b->base); delete b; return cc_fail(dev, CC_ERR_CUDA, "upload: %s", cudaGetErrorString(e)); }
+        *out = b;
+        return CC_OK;
+    }
+    // quantized: stage the GGUF bytes on device, repack into planes, drop the staging copy
+    b->bytes = cc_device_layout_bytes(t, rows, cols);
+    uint8_t* staging = nullptr;
+    cudaError_t e = cudaMalloc(&b->base, b->bytes ? b->bytes : 1);
+    if (e == cudaSuccess) e = cudaMalloc(&staging, need ? need : 1);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(staging, bytes, need, cudaMemcpyHostToDevice, dev->stream);
+    if (e != cudaSuccess) {
+        if (b->base) cudaFree(b->base);
+        if (staging) cudaFree(staging);
+        delete b;
+        return cc_fail(dev, CC_ERR_CUDA, "from_cpu upload (%zu bytes): %s", need, cudaGetErrorString(e));
+    }
+    cc_assign_planes(b);
+    int rc = cc_launch_repack(dev, staging, b);
+    cudaError_t e2 = cudaStreamSynchronize(dev->stream);
+    cudaFree(staging);
+    if (rc == CC_OK && e2 != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "repack: %s", cudaGetErrorString(e2));
+    if (rc != CC_OK) { cudaFree(b->base); delete b; return rc; }
+    *out = b;
+    return CC_OK;
+}
+
+extern "C" CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t t, uint64_t seed,
+                               uint64_t tensor_id, float scale, cc_buf** out) {
+    if (!dev || !shape || !out || ndim < 1 || ndim > CC_MAX_DIMS) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_synth: bad argument");
+    int be = cc_block_elems(t);
+    CC_REQUIRE(dev, be > 1, "synth: quantized types only, got %d", t);
+    int64_t n = prod(shape, ndim);
+    int64_t cols = shape[ndim - 1], rows = n / cols;
+    CC_REQUIRE(dev, cols % be == 0, "synth: last dim %lld is not a multiple of the block", (long long)cols);
+    size_t need = (size_t)(n / be) * cc_block_bytes(t);
+    cc_buf* b = new cc_buf();
+    b->dev = dev; b->dtype = t; b->nelems = n; b->rows = rows; b->cols = cols;
+    b->bytes = cc_device_layout_bytes(t, rows, cols);
+    uint8_t* staging = nullptr;
+    cudaError_t e = cudaMalloc(&b->base, b->bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&staging, need);
+    if (e != cudaSuccess) {
+        if (b->base) cudaFree(b->base);
+        delete b;
+        return cc_fail(dev, CC_ERR_CUDA, "synth alloc: %s", cudaGetErrorString(e));
+    }
+    cc_assign_planes(b);
+    int rc = cc_launch_synth(dev, staging, t, n / be, seed, tensor_id, scale);
+    if (rc == CC_OK) rc = cc_launch_repack(dev, staging, b);
+    cudaError_t e2 = cudaStreamSynchronize(dev->stream);
+    cudaFree(staging);
+    if (rc == CC_OK && e2 != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "synth: %s", cudaGetErrorString(e2));
+    if (rc != CC_OK) { cudaFree(b->base); delete b; return rc; }
+    *out = b;
+    return CC_OK;
+}
+
+extern "C" CC_API int cc_test_export_blocks(cc_device* dev, const cc_buf* buf, void* dst, size_t nbytes) {
+    if (!dev || !buf || !dst) return cc_fail(dev, CC_ERR_ARG, "cc_test_export_blocks: bad argument");
+    CC_REQUIRE(dev, cc_is_quant(buf->dtype), "export_blocks: not a quantized tensor");
+    size_t need = (size_t)(buf->nelems / cc_block_elems(buf->dtype)) * cc_block_bytes(buf->dtype);
+    CC_REQUIRE(dev, nbytes >= need, "export_blocks: %zu bytes given, %zu needed", nbytes, need);
+    uint8_t* staging = nullptr;
+    CC_CUDA(dev, cudaMalloc(&staging, need));
+    int rc = cc_launch_unrepack(dev, buf, staging);
+    if (rc == CC_OK) {
+        cudaError_t e = cudaMemcpyAsync(dst, staging, need, cudaMemcpyDeviceToHost, dev->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
+        if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "export_blocks: %s", cudaGetErrorString(e));
+    }
+    cudaFree(staging);
+    return rc;
+}

@@ -1,0 +1,317 @@
+// repack.cu -- GGUF AoS blocks <-> device planes, row dequantisation (copy_rows_from), synthetic weights.
+//
+// Block field orders follow the reference structs:
+//   Q8_0 buf_q8_0.rs:8-13 | Q4_0 buf_q4_0.rs:10-15 | Q4_1 buf_q4_1.rs:10-16 | Q5_0 buf_q5_0.rs:13-19
+//   Q5_1 buf_q5_1.rs:10-17 | Q2_K buf_q2_k.rs:17-28 | Q3_K buf_q3_k.rs:19-30 | Q4_K buf_q4_k.rs:14-21
+//   Q5_K ggml order d,dmin,scales,qh,qs (the reference struct buf_q5_k.rs:15-21 is wrong, B9)
+//   Q6_K buf_q6_k.rs:11-18 | Q8_K buf_q8_k.rs:6-12
+#include "common.cuh"
+
+struct PlaneSpec { int bytes[CC_MAX_PLANES]; int src_off[CC_MAX_PLANES]; int n; };
+
+// per-block bytes of each plane and the offset of that field inside the GGUF block
+static PlaneSpec plane_spec(int t) {
+    switch (t) {
+    case CC_Q8_0: return {{32, 2, 0, 0}, {2, 0, 0, 0}, 2};
+    case CC_Q4_0: return {{16, 2, 0, 0}, {2, 0, 0, 0}, 2};
+    case CC_Q4_1: return {{16, 4, 0, 0}, {4, 0, 0, 0}, 2};
+    case CC_Q5_0: return {{16, 2, 4, 0}, {6, 0, 2, 0}, 3};
+    case CC_Q5_1: return {{16, 4, 4, 0}, {8, 0, 4, 0}, 3};
+    case CC_Q2_K: return {{64, 16, 4, 0}, {16, 0, 80, 0}, 3};
+    case CC_Q3_K: return {{64, 32, 12, 2}, {32, 0, 96, 108}, 4};
+    case CC_Q4_K: return {{144, 0, 0, 0}, {0, 0, 0, 0}, 1};
+    case CC_Q5_K: return {{176, 0, 0, 0}, {0, 0, 0, 0}, 1};
+    case CC_Q6_K: return {{128, 64, 16, 2}, {0, 128, 192, 208}, 4};
+    case CC_Q8_K: return {{256, 4, 0, 0}, {4, 0, 0, 0}, 2};     // bsums are activation-only and dropped
+    case CC_Q8_1: return {{32, 4, 0, 0}, {4, 0, 0, 0}, 2};
+    }
+    return {{0, 0, 0, 0}, {0, 0, 0, 0}, 0};
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t cc_device_layout_bytes(int t, int64_t rows, int64_t cols) {
+    PlaneSpec ps = plane_spec(t);
+    int64_t nblk = rows * (cols / cc_block_elems(t));
+    size_t total = 0;
+    for (int p = 0; p < ps.n; p++) total += align256((size_t)nblk * ps.bytes[p]);
+    return total ? total : 256;
+}
+
+void cc_assign_planes(cc_buf* b) {
+    PlaneSpec ps = plane_spec(b->dtype);
+    int64_t nblk = b->nelems / cc_block_elems(b->dtype);
+    uint8_t* p = (uint8_t*)b->base;
+    for (int i = 0; i < ps.n; i++) {
+        b->plane[i] = p;
+        p += align256((size_t)nblk * ps.bytes[i]);
+    }
+}
+
+struct RepackArgs {
+    uint8_t* plane[CC_MAX_PLANES];
+    int bytes[CC_MAX_PLANES];
+    int src_off[CC_MAX_PLANES];
+    int n;
+    int block_bytes;
+};
+
+// one thread per (block, plane byte): trivially parallel, load-time only
+template <bool TO_PLANES>
+__global__ void repack_kernel(uint8_t* gguf, RepackArgs a, int64_t nblk, int plane) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int pb = a.bytes[plane];
+    if (i >= nblk * pb) return;
+    int64_t blk = i / pb;
+    int j = (int)(i - blk * pb);
+    uint8_t* g = gguf + blk * a.block_bytes + a.src_off[plane] + j;
+    uint8_t* p = a.plane[plane] + i;
+    if (TO_PLANES) *p = *g; else *g = *p;
+}
+
+static RepackArgs make_args(const cc_buf* b) {
+    PlaneSpec ps = plane_spec(b->dtype);
+    RepackArgs a;
+    a.n = ps.n;
+    a.block_bytes = (int)cc_block_bytes(b->dtype);
+    for (int i = 0; i < CC_MAX_PLANES; i++) { a.plane[i] = b->plane[i]; a.bytes[i] = ps.bytes[i]; a.src_off[i] = ps.src_off[i]; }
+    return a;
+}
+
+int cc_launch_repack(cc_device* dev, const uint8_t* gguf_dev, cc_buf* dst) {
+    RepackArgs a = make_args(dst);
+    int64_t nblk = dst->nelems / cc_block_elems(dst->dtype);
+    for (int p = 0; p < a.n; p++) {
+        int64_t total = nblk * a.bytes[p];
+        if (total == 0) continue;
+        repack_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, dev->stream>>>((uint8_t*)gguf_dev, a, nblk, p);
+        CC_LAUNCH_CHECK(dev);
+    }
+    return CC_OK;
+}
+
+int cc_launch_unrepack(cc_device* dev, const cc_buf* src, uint8_t* gguf_dev) {
+    RepackArgs a = make_args(src);
+    int64_t nblk = src->nelems / cc_block_elems(src->dtype);
+    CC_CUDA(dev, cudaMemsetAsync(gguf_dev, 0, (size_t)nblk * a.block_bytes, dev->stream));
+    for (int p = 0; p < a.n; p++) {
+        int64_t total = nblk * a.bytes[p];
+        if (total == 0) continue;
+        repack_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, dev->stream>>>(gguf_dev, a, nblk, p);
+        CC_LAUNCH_CHECK(dev);
+    }
+    return CC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Element-wise dequantisation from the device planes: BlockQ*::dequantize (cited per type).
+// Association of the float products follows the reference so results are BIT-EXACT
+// (file compiled with -fmad=false).
+// ---------------------------------------------------------------------------------------------------
+struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; };
+
+__device__ __forceinline__ void get_scale_min_k4(int j, const uint8_t* q, uint8_t* d, uint8_t* m) {   // util.rs:18-27
+    if (j < 4) {
+        *d = q[j] & 63;
+        *m = q[j + 4] & 63;
+    } else {
+        *d = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4);
+        *m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4);
+    }
+}
+
+// value of element `e` (0-based within the whole tensor, row-major)
+__device__ float dequant_elem(int t, const DeqPlanes& P, int64_t e) {
+    switch (t) {
+    case CC_Q8_0: {                                                        // buf_q8_0.rs:18-23
+        int64_t b = e >> 5;
+        float d = h2f_bits(((const uint16_t*)P.p[1])[b]);
+        return (float)((const int8_t*)P.p[0])[e] * d;
+    }
+    case CC_Q4_0: {                                                        // buf_q4_0.rs:18-27
+        int64_t b = e >> 5; int i = (int)(e & 31);
+        uint8_t q = P.p[0][b * 16 + (i & 15)];
+        int x = (i < 16 ? (q & 0x0F) : (q >> 4)) - 8;
+        return (float)x * h2f_bits(((const uint16_t*)P.p[1])[b]);
+    }
+    case CC_Q4_1: {                                                        // vec_dot order, buf_q4_1.rs:266-280 (B10)
+        int64_t b = e >> 5; int i = (int)(e & 31);
+        uint8_t q = P.p[0][b * 16 + (i & 15)];
+        float x = (float)(i < 16 ? (q & 0x0F) : (q >> 4));
+        const uint16_t* dm = (const uint16_t*)P.p[1] + b * 2;
+        return x * h2f_bits(dm[0]) + h2f_bits(dm[1]);
+    }
+    case CC_Q5_0: {                                                        // buf_q5_0.rs:22-37
+        int64_t b = e >> 5; int i = (int)(e & 31);
+        uint8_t q = P.p[0][b * 16 + (i & 15)];
+        uint32_t qh = ((const uint32_t*)P.p[2])[b];
+        int x = (int)((i < 16 ? (q & 0x0F) : (q >> 4)) | (((qh >> i) & 1) << 4)) - 16;
+        return (float)x * h2f_bits(((const uint16_t*)P.p[1])[b]);
+    }
+    case CC_Q5_1: {                                                        // buf_q5_1.rs:20-37
+        int64_t b = e >> 5; int i = (int)(e & 31);
+        uint8_t q = P.p[0][b * 16 + (i & 15)];
+        uint32_t qh = ((const uint32_t*)P.p[2])[b];
+        float x = (float)((i < 16 ? (q & 0x0F) : (q >> 4)) | (((qh >> i) & 1) << 4));
+        const uint16_t* dm = (const uint16_t*)P.p[1] + b * 2;
+        return x * h2f_bits(dm[0]) + h2f_bits(dm[1]);
+    }
+    case CC_Q2_K: {                                                        // buf_q2_k.rs:35-69
+        int64_t b = e >> 8; int i = (int)(e & 255);
+        int half = i >> 7, r = i & 127, j = r >> 5, l = r & 31;            // 128-half, shift group j, byte l
+        uint8_t sc = P.p[1][b * 16 + half * 8 + j * 2 + (l >> 4)];
+        const uint16_t* dd = (const uint16_t*)P.p[2] + b * 2;
+        float dl = h2f_bits(dd[0]) * (float)(sc & 0xF), ml = h2f_bits(dd[1]) * (float)(sc >> 4);
+        uint8_t q = P.p[0][b * 64 + half * 32 + l];
+        return dl * (float)((q >> (2 * j)) & 3) - ml;
+    }
+    case CC_Q3_K: {                                                        // buf_q3_k.rs:37-84
+        int64_t b = e >> 8; int i = (int)(e & 255);
+        int half = i >> 7, r = i & 127, j = r >> 5, l = r & 31;
+        const uint8_t* s12 = P.p[2] + b * 12;
+        int is = half * 8 + j * 2 + (l >> 4);
+        // 6-bit scale `is` out of the 12 packed bytes (kmask shuffle of buf_q3_k.rs:44-58)
+        int lo = is < 8 ? (s12[is] & 0xF) : (s12[is - 8] >> 4);
+        int hi = (s12[8 + (is & 3)] >> (2 * (is >> 2))) & 3;
+        int scale = (int)(int8_t)(lo | (hi << 4)) - 32;
+        float dl = h2f_bits(((const uint16_t*)P.p[3])[b]) * (float)scale;
+        uint8_t m = (uint8_t)(1u << (half * 4 + j));
+        int mm = (P.p[1][b * 32 + l] & m) ? 0 : 4;
+        uint8_t q = P.p[0][b * 64 + half * 32 + l];
+        return dl * (float)((int)((q >> (2 * j)) & 3) - mm);
+    }
+    case CC_Q4_K: {                                                        // buf_q4_k.rs:24-48
+        int64_t b = e >> 8; int i = (int)(e & 255);
+        const uint8_t* blk = P.p[0] + b * 144;
+        int c = i >> 6, r = i & 63, l = r & 31, hi = r >> 5;
+        uint8_t sc, m;
+        get_scale_min_k4(2 * c + hi, blk + 4, &sc, &m);
+        float d = h2f_bits(*(const uint16_t*)blk) * (float)sc, mn = h2f_bits(*(const uint16_t*)(blk + 2)) * (float)m;
+        uint8_t q = blk[16 + 32 * c + l];
+        return d * (float)(hi ? (q >> 4) : (q & 0xF)) - mn;
+    }
+    case CC_Q5_K: {                                                        // buf_q5_k.rs:23-59 on the ggml field order
+        int64_t b = e >> 8; int i = (int)(e & 255);
+        const uint8_t* blk = P.p[0] + b * 176;
+        int c = i >> 6, r = i & 63, l = r & 31, hi = r >> 5;
+        uint8_t sc, m;
+        get_scale_min_k4(2 * c + hi, blk + 4, &sc, &m);
+        float d = h2f_bits(*(const uint16_t*)blk) * (float)sc, mn = h2f_bits(*(const uint16_t*)(blk + 2)) * (float)m;
+        uint8_t q = blk[48 + 32 * c + l];
+        uint8_t qh = blk[16 + l];
+        float v = (float)(hi ? (q >> 4) : (q & 0xF)) + ((qh & (1u << (2 * c + hi))) ? 16.0f : 0.0f);
+        return d * v - mn;
+    }
+    case CC_Q6_K: {                                                        // buf_q6_k.rs:21-47
+        int64_t b = e >> 8; int i = (int)(e & 255);
+        int half = i >> 7, r = i & 127, g = r >> 5, l = r & 31;            // g: q1..q4
+        const uint8_t* ql = P.p[0] + b * 128 + 64 * half;
+        uint8_t qh = P.p[1][b * 64 + 32 * half + l];
+        int8_t sc = ((const int8_t*)P.p[2])[b * 16 + 8 * half + (l >> 4) + 2 * g];
+        uint8_t lo = (g & 1) ? ql[l + 32] : ql[l];
+        int nib = (g >= 2) ? (lo >> 4) : (lo & 0xF);
+        int q = (int)(int8_t)(nib | (((qh >> (2 * g)) & 3) << 4)) - 32;
+        float d = h2f_bits(((const uint16_t*)P.p[3])[b]);
+        return d * (float)sc * (float)q;
+    }
+    case CC_Q8_K: {                                                        // buf_q8_k.rs:15-20
+        int64_t b = e >> 8;
+        return ((const float*)P.p[1])[b] * (float)((const int8_t*)P.p[0])[e];
+    }
+    }
+    return 0.0f;
+}
+
+__global__ void dequant_rows_kernel(int t, DeqPlanes P, const int64_t* rows, int n_rows, int64_t cols,
+                                    float* dst_f32, __half* dst_f16) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_rows * cols) return;
+    int64_t r = i / cols, c = i - r * cols;
+    int64_t e = rows[r] * cols + c;
+    float v;
+    if (t == CC_F32) v = ((const float*)P.p[0])[e];
+    else if (t == CC_F16) v = __half2float(((const __half*)P.p[0])[e]);
+    else v = dequant_elem(t, P, e);
+    if (dst_f32) dst_f32[i] = v; else dst_f16[i] = __float2half_rn(v);
+}
+
+int cc_launch_dequant_rows(cc_device* dev, const cc_buf* src, const int64_t* rows_dev, int n_rows, int64_t cols,
+                           void* dst, int dst_dtype) {
+    DeqPlanes P;
+    for (int i = 0; i < CC_MAX_PLANES; i++) P.p[i] = src->plane[i];
+    int64_t total = (int64_t)n_rows * cols;
+    if (total == 0) return CC_OK;
+    dequant_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, dev->stream>>>(
+        src->dtype, P, rows_dev, n_rows, cols, dst_dtype == CC_F32 ? (float*)dst : nullptr,
+        dst_dtype == CC_F16 ? (__half*)dst : nullptr);
+    CC_LAUNCH_CHECK(dev);
+    return CC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Synthetic weights: counter-based splitmix64 over (seed, tensor, byte index)
+// written in GGUF block layout, f16 scale fields overwritten with log-uniform one-octave-wide values.
+// tests/synth.py holds the identical CPU generator.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+struct SynthSpec { int n_f16; int off[2]; int is_min[2]; int d_f32_off; };
+
+static SynthSpec synth_spec(int t) {
+    switch (t) {
+    case CC_Q8_0: case CC_Q4_0: case CC_Q5_0: return {1, {0, 0}, {0, 0}, -1};
+    case CC_Q4_1: case CC_Q5_1: return {2, {0, 2}, {0, 1}, -1};
+    case CC_Q2_K: return {2, {80, 82}, {0, 1}, -1};
+    case CC_Q3_K: return {1, {108, 0}, {0, 0}, -1};
+    case CC_Q4_K: case CC_Q5_K: return {2, {0, 2}, {0, 1}, -1};
+    case CC_Q6_K: return {1, {208, 0}, {0, 0}, -1};
+    case CC_Q8_K: return {0, {0, 0}, {0, 0}, 0};
+    }
+    return {0, {0, 0}, {0, 0}, -1};
+}
+
+__global__ void synth_kernel(uint8_t* out, int64_t nblocks, int bb, SynthSpec sp, uint64_t key, float scale) {
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 output bytes
+    int64_t total = nblocks * bb;
+    int64_t base = w * 8;
+    if (base >= total) return;
+    uint64_t r = splitmix64(key ^ (uint64_t)w);
+    for (int j = 0; j < 8 && base + j < total; j++) out[base + j] = (uint8_t)(r >> (8 * j));
+}
+__global__ void synth_scales_kernel(uint8_t* out, int64_t nblocks, int bb, SynthSpec sp, uint64_t key, float scale) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    uint64_t r = splitmix64(key ^ 0xD1B54A32D192ED03ull ^ (uint64_t)b);
+    for (int f = 0; f < sp.n_f16; f++) {
+        // log-uniform in [scale/sqrt2, scale*sqrt2): one octave wide; mins get a random sign
+        float u = (float)((r >> (16 * f)) & 0xFFFF) * (1.0f / 65536.0f);
+        float v = scale * exp2f(u - 0.5f);
+        if (sp.is_min[f]) v *= 0.25f;
+        uint16_t h = f2h_bits(v);
+        out[b * bb + sp.off[f]] = (uint8_t)(h & 0xFF);
+        out[b * bb + sp.off[f] + 1] = (uint8_t)(h >> 8);
+    }
+    if (sp.d_f32_off >= 0) {
+        float u = (float)(r & 0xFFFF) * (1.0f / 65536.0f);
+        float v = scale * exp2f(u - 0.5f);
+        uint32_t bits = __float_as_uint(v);
+        for (int j = 0; j < 4; j++) out[b * bb + sp.d_f32_off + j] = (uint8_t)(bits >> (8 * j));
+    }
+}
+
+int cc_launch_synth(cc_device* dev, uint8_t* gguf_dev, int t, int64_t nblocks, uint64_t seed, uint64_t tid, float scale) {
+    int bb = (int)cc_block_bytes(t);
+    SynthSpec sp = synth_spec(t);
+    uint64_t key = splitmix64(seed ^ splitmix64(tid));
+    int64_t words = (nblocks * bb + 7) / 8;
+    synth_kernel<<<(unsigned)((words + 255) / 256), 256, 0, dev->stream>>>(gguf_dev, nblocks, bb, sp, key, scale);
+    CC_LAUNCH_CHECK(dev);
+    synth_scales_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, dev->stream>>>(gguf_dev, nblocks, bb, sp, key, scale);
+    CC_LAUNCH_CHECK(dev);
+    return CC_OK;
+}

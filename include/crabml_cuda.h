@@ -1,0 +1,146 @@
+/*
+ * crabml_cuda.h -- C ABI of the B200-native CUDA backend for crabml's quantized tensor-op path.
+ *
+ * This is the drop-in boundary: one entry point per method of the reference's `Tensor` trait
+ * (crabml-core/src/tensor/api.rs:11-79).  A Rust `crabml-cuda` crate binds these with
+ * `extern "C"`; in this repo they are driven by the C++ host mirror
+ * (crabml_b200/csrc/host/) and by Python ctypes in tests/ and bench.py.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  No torch types, no C++ types, nothing throws.
+ *  - Every function returns a status: 0 = ok, non-zero = error.  CC_ERR_TENSOR maps to the
+ *    reference's ErrorKind::TensorError (crabml-core/src/error.rs:24-25); the message is
+ *    available from cc_last_error().  Internal invariant violations that are `assert!`s in the
+ *    reference (e.g. primitives/matmul_vec.rs:17-19) are reported as CC_ERR_TENSOR too.
+ *  - A tensor on the Rust side is {Arc<buffer>, TensorStrider, device, name}
+ *    (cf. crabml-wgpu/src/wgpu_tensor.rs:20-28).  The strider stays host-side: metadata-only
+ *    trait methods (reshape / transpose / with_strider / resize / shape / strider,
+ *    api.rs:28-44) never cross this ABI.  Ops take a `cc_view` = buffer handle + the strider's
+ *    shape and strides (in elements).
+ *  - All work is enqueued on the device's single stream; only cc_tensor_export_f32,
+ *    cc_debug_tensor_tap and cc_device_synchronize block (api.rs:52; llama2.rs:209).
+ *  - There is NO CPU fallback: without a CUDA device cc_device_create fails.
+ */
+#ifndef CRABML_CUDA_H
+#define CRABML_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CC_API __attribute__((visibility("default")))
+#else
+#define CC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_OK 0
+#define CC_ERR_TENSOR 1   /* ErrorKind::TensorError */
+#define CC_ERR_CUDA 2     /* a CUDA runtime call failed (text in cc_last_error) */
+#define CC_ERR_ARG 3      /* NULL / malformed argument */
+#define CC_ERR_UNSUPPORTED 4
+
+/* GGMLType ids, crabml-core/src/gguf.rs:86-108 */
+enum cc_ggml_type {
+    CC_F32 = 0, CC_F16 = 1, CC_Q4_0 = 2, CC_Q4_1 = 3, CC_Q5_0 = 6, CC_Q5_1 = 7,
+    CC_Q8_0 = 8, CC_Q8_1 = 9, CC_Q2_K = 10, CC_Q3_K = 11, CC_Q4_K = 12,
+    CC_Q5_K = 13, CC_Q6_K = 14, CC_Q8_K = 15
+};
+
+/* RopeMode, api.rs:5-9 */
+enum cc_rope_mode { CC_ROPE_LLAMA = 0, CC_ROPE_NEOX = 1 };
+
+#define CC_MAX_DIMS 4
+
+typedef struct cc_device cc_device;   /* T::DeviceRef */
+typedef struct cc_buf cc_buf;         /* refcounted device storage (the Arc<Buffer> of a tensor) */
+
+/* TensorStrider (crabml-core/src/tensor/strider.rs:5-9) passed by value with the buffer. */
+typedef struct cc_view {
+    cc_buf* buf;
+    int32_t ndim;
+    int64_t shape[CC_MAX_DIMS];
+    int64_t strides[CC_MAX_DIMS];   /* in elements */
+} cc_view;
+
+/* CpuTensorDeviceOptions / WgpuTensorDeviceOptions analogue (cpu_device.rs:13-48). */
+typedef struct cc_device_options {
+    int32_t device_ordinal;        /* CUDA device index */
+    int32_t debug_named_tensors;   /* with_name() snapshots tensors to host (cpu_tensor.rs:232-241) */
+    int32_t lazy;                  /* 0 = eager: one launch per trait call; 1 = record + fuse + CUDA-graph replay */
+    int32_t reserved;
+    uint64_t pool_bytes;           /* activation pool size hint, 0 = default */
+} cc_device_options;
+
+/* ---- device ---------------------------------------------------------------------------- */
+CC_API int cc_device_create(const cc_device_options* opts, cc_device** out);
+CC_API void cc_device_destroy(cc_device* dev);
+CC_API const char* cc_last_error(cc_device* dev);          /* NULL dev: last creation error */
+CC_API int cc_device_synchronize(cc_device* dev);
+/* counters: kernels launched by this library since creation (bench.py "gpu_launches") */
+CC_API uint64_t cc_device_launch_count(cc_device* dev);
+/* raw cudaStream_t of the device, for event timing by the caller */
+CC_API void* cc_device_stream(cc_device* dev);
+
+/* ---- storage: Tensor::from_cpu / alloc / Clone / Drop (api.rs:14-23) -------------------- */
+/* from_cpu: copies `nbytes` host bytes of GGUF-layout data (row-major rows of quant blocks,
+ * model.rs:462-477).  `shape` is [rows, cols] (or 1-D).  Quantized types are repacked once
+ * into the device layout documented in DESIGN.md (same algorithmic bytes). */
+CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size_t nbytes, const int64_t* shape,
+                       int32_t ndim, int32_t ggml_type, cc_buf** out);
+/* alloc: F32 zero-filled, or F16 (cpu_tensor.rs:138-165); other dtypes -> CC_ERR_TENSOR */
+CC_API int cc_tensor_alloc(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t ggml_type, cc_buf** out);
+CC_API void cc_tensor_retain(cc_buf* buf);
+CC_API void cc_tensor_release(cc_buf* buf);
+CC_API int32_t cc_tensor_dtype(const cc_buf* buf);          /* api.rs:30 */
+CC_API int64_t cc_tensor_capacity(const cc_buf* buf);       /* elements of backing storage (resize bound, cpu_tensor.rs:180) */
+
+/* ---- data movement ------------------------------------------------------------------------ */
+CC_API int cc_tensor_dup(cc_device* dev, const cc_view* src, cc_buf** out);                 /* api.rs:55 */
+CC_API int cc_tensor_export_f32(cc_device* dev, const cc_view* src, float* dst, size_t n);  /* api.rs:52 */
+CC_API int cc_copy_rows_from(cc_device* dev, const cc_view* dst, const cc_view* src,
+                      const int64_t* rows, int32_t n_rows);                          /* api.rs:50 */
+/* concatenate writes rhs at offset shape[axis] along `axis` using self's strides
+ * (concatenate.rs:12-77); the caller then bumps its strider's shape[axis]. */
+CC_API int cc_concatenate(cc_device* dev, const cc_view* self, const cc_view* rhs, int32_t axis);  /* api.rs:46 */
+CC_API int cc_contiguous(cc_device* dev, const cc_view* src, cc_buf** out);                 /* api.rs:40 */
+
+/* ---- in-place elementwise ops (api.rs:57-74) ---------------------------------------------- */
+CC_API int cc_rope_inplace(cc_device* dev, const cc_view* x, int32_t mode, int64_t pos, int64_t rope_dims);
+CC_API int cc_rms_norm_inplace(cc_device* dev, const cc_view* x, float eps);
+CC_API int cc_softmax_inplace(cc_device* dev, const cc_view* x, int32_t axis);
+CC_API int cc_silu_inplace(cc_device* dev, const cc_view* x);
+CC_API int cc_gelu_inplace(cc_device* dev, const cc_view* x);
+CC_API int cc_mul_inplace(cc_device* dev, const cc_view* x, const cc_view* rhs);
+CC_API int cc_add_inplace(cc_device* dev, const cc_view* x, const cc_view* rhs);
+CC_API int cc_scale_inplace(cc_device* dev, const cc_view* x, float rhs);
+
+/* ---- the hot path (api.rs:76-78) ------------------------------------------------------------ */
+/* matmul_vec: W (m,k) any dtype, x F32 (k,) or (b,k) -> new F32 (m,) / (b,m).
+ * The activation is quantized on the fly to W's partner type (buf/api.rs:142-159). */
+CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_view* x, cc_buf** out);
+CC_API int cc_batch_matmul(cc_device* dev, const cc_view* a, const cc_view* b, cc_buf** out);
+
+/* ---- debug tap: with_name / dump_debug_tensor (cpu_tensor.rs:232-241, cpu_device.rs:96-98) -- */
+CC_API int cc_debug_tensor_tap(cc_device* dev, const char* name, const cc_view* x);
+/* returns element count via *n; copies min(*n_in, count) floats when dst != NULL */
+CC_API int cc_dump_debug_tensor(cc_device* dev, const char* name, float* dst, size_t* n);
+
+/* ---- test / bench hooks (not part of the trait) ---------------------------------------------- */
+/* quantize an F32 vector exactly as matmul_vec does internally and return the reference-layout
+ * activation blocks (Q8_0 / Q8_1 / Q8_K bytes) to the host: parity tests of a3-a5. */
+CC_API int cc_test_quantize_activation(cc_device* dev, const cc_view* x, int32_t act_type, void* dst, size_t nbytes);
+/* synthetic weights generated on device in the device layout: counter-based
+ * RNG, identical bytes to tests/synth.py's CPU generator for the same (seed, tensor_id). */
+CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t ggml_type,
+                    uint64_t seed, uint64_t tensor_id, float scale, cc_buf** out);
+/* copy a quantized tensor back in GGUF block layout (inverse of the load-time repack) */
+CC_API int cc_test_export_blocks(cc_device* dev, const cc_buf* buf, void* dst, size_t nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRABML_CUDA_H */

@@ -1,0 +1,73 @@
+"""End-to-end parity on the reference's own GGUF fixtures: the Llama2Runner replay
+(llama2.rs:184-281,527-638) over CudaTensor vs the same replay over the CPU oracle.
+north_star: logits within 1e-3 relative; golden generations of llama2.rs:673-703 reproduced."""
+import numpy as np
+import pytest
+
+from oracle import oracle as oc
+from oracle.llama_replay import GGUFModel, Llama2Runner, LlamaTokenizer, decode_text, load_weights
+from oracle.tensor_ref import OracleDevice, OracleTensor
+from tests.gpu_common import make_device
+from tests.test_oracle_golden_text import CASES, PROMPT, PROMPT_IDS
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3      # north_star bar (relative to max |logit|)
+
+
+def _run(T, dev, gm, steps, f16_kv=False):
+    w = load_weights(gm, T, dev)
+    r = Llama2Runner(T, gm.conf, w, dev, 200, use_f16_kv_cache=f16_kv)
+    logits = []
+    pos, _, t0 = r.prefill(PROMPT_IDS)
+    logits.append(r.logits.copy())
+    out = []
+    for t in r.generate(pos, t0, steps, eos=gm.eos):
+        out.append(t)
+        logits.append(r.logits.copy())
+    return out, np.stack(logits)
+
+
+@pytest.mark.parametrize("fname,text,ids", CASES)
+@pytest.mark.parametrize("f16_kv", [False, True])
+def test_generation_and_logits_parity(fixture_path, fname, text, ids, f16_kv):
+    from crabml_b200 import CudaTensor
+    gm = GGUFModel(fixture_path(fname))
+    tok = LlamaTokenizer(gm.tokens, gm.scores, gm.bos, gm.eos)
+    assert tok.encode(PROMPT, True, False) == PROMPT_IDS
+    gdev = make_device(debug_named_tensors=True)
+    odev = OracleDevice(debug_named_tensors=True)
+    try:
+        g_out, g_logits = _run(CudaTensor, gdev, gm, 11, f16_kv)
+        o_out, o_logits = _run(OracleTensor, odev, gm, 11, f16_kv)
+        assert g_out == o_out
+        if not f16_kv or "q8_0" in fname:                     # llama2.rs:673-719 golden strings
+            assert g_out == ids and decode_text(tok, g_out) == text
+        scale = np.abs(o_logits).max(axis=1, keepdims=True)
+        rel = (np.abs(g_logits - o_logits) / scale).max()
+        assert rel < REL_TOL, rel
+        # debug tap parity, the mechanism of the reference's own cross-backend test (llama2.rs:768-784)
+        for name, eps in (("attn_rmsnorm:0:0", 1e-6), ("x_debug:0:0", 1e-6), ("attn_out:0:0", 1e-4), ("ffn_out:5:9", 1e-3), ("final_rmsnorm:9", 1e-3)):
+            a, b = gdev.dump_debug_tensor(name), odev.dump_debug_tensor(name)
+            assert a is not None and a.shape == b.shape, name
+            np.testing.assert_allclose(a, b, atol=eps * max(1.0, float(np.abs(b).max())), err_msg=name)
+        print(f"{fname} f16_kv={f16_kv}: max rel logits diff {rel:.3e}")
+    finally:
+        gdev.close()
+
+
+def test_long_decode_positions(fixture_path):
+    """100 decode steps (BASELINE config 1/2): positions up to ~110 exercise the RoPE recurrence and
+    a growing KV cache; logits must stay within the bar at every step."""
+    from crabml_b200 import CudaTensor
+    gm = GGUFModel(fixture_path("tinyllamas-stories-15m-q8_0.gguf"))
+    gdev = make_device()
+    try:
+        g_out, g_logits = _run(CudaTensor, gdev, gm, 100)
+        o_out, o_logits = _run(OracleTensor, OracleDevice(), gm, 100)
+        n = min(len(g_logits), len(o_logits))
+        assert g_out[:n - 1] == o_out[:n - 1]
+        rel = (np.abs(g_logits[:n] - o_logits[:n]) / np.abs(o_logits[:n]).max(axis=1, keepdims=True)).max()
+        assert rel < REL_TOL, rel
+    finally:
+        gdev.close()
