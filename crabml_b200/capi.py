@@ -32,7 +32,7 @@ class cc_view(C.Structure):
 
 class cc_device_options(C.Structure):
     _fields_ = [("device_ordinal", C.c_int32), ("debug_named_tensors", C.c_int32), ("lazy", C.c_int32),
-                ("reserved", C.c_int32), ("pool_bytes", C.c_uint64)]
+                ("exact_order", C.c_int32), ("pool_bytes", C.c_uint64)]
 
 
 def declared_symbols():

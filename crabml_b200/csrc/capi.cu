@@ -141,7 +141,9 @@ extern "C" CC_API int cc_rope_inplace(cc_device* dev, const cc_view* x, int32_t 
     if (x->ndim == 2) { n_batch = 1; stride = view_len(x); hd = x->shape[1]; }
     else { n_batch = x->shape[0]; stride = x->strides[0]; hd = x->shape[2]; }
     CC_REQUIRE(dev, rope_dims >= 0 && rope_dims <= hd && rope_dims % 2 == 0, "rope_inplace: bad rope_dims %lld", (long long)rope_dims);
-    return cc_launch_rope(dev, (float*)x->buf->plane[0], n_batch, stride, hd, mode, pos, rope_dims);
+    // cos/sin are evaluated on the host with the same libm calls as the reference (rope.rs:52-53,74-75) in both
+    // modes: bit-exact, and no slow large-argument device sinf/cosf
+    return cc_launch_rope_exact(dev, (float*)x->buf->plane[0], n_batch, stride, hd, mode, pos, rope_dims);
 }
 
 extern "C" CC_API int cc_rms_norm_inplace(cc_device* dev, const cc_view* x, float eps) {    // rms_norm.rs:9-30
@@ -151,6 +153,7 @@ extern "C" CC_API int cc_rms_norm_inplace(cc_device* dev, const cc_view* x, floa
     REQUIRE_F32(dev, x, "rms_norm_inplace");
     int64_t rows = x->ndim == 1 ? 1 : x->shape[0], cols = x->ndim == 1 ? x->shape[0] : x->shape[1];
     CC_REQUIRE(dev, cols % 32 == 0, "rms_norm_inplace: length %lld %% 32 != 0", (long long)cols);   // rms_norm.rs:34
+    if (dev->exact) return cc_launch_rms_norm_exact(dev, (float*)x->buf->plane[0], rows, cols, eps);
     return cc_launch_rms_norm(dev, (float*)x->buf->plane[0], rows, cols, eps);
 }
 
@@ -161,6 +164,7 @@ extern "C" CC_API int cc_softmax_inplace(cc_device* dev, const cc_view* x, int32
     REQUIRE_F32(dev, x, "softmax_inplace");
     CC_REQUIRE(dev, axis == x->ndim - 1, "only axis=%d is supported on a %d dimensions tensor", x->ndim - 1, x->ndim);
     int64_t cols = x->shape[x->ndim - 1];
+    if (dev->exact) return cc_launch_softmax_exact(dev, (float*)x->buf->plane[0], cols ? view_len(x) / cols : 0, cols);
     return cc_launch_softmax(dev, (float*)x->buf->plane[0], cols ? view_len(x) / cols : 0, cols);
 }
 
@@ -224,7 +228,19 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
         rc = cc_ensure_act_scratch(dev, cc_act_bytes(at, b * k));
         if (!rc) rc = cc_launch_quantize(dev, xf, b * k, at, dev->act_scratch);     // matmul_vec.rs:37-40
     }
-    if (!rc) rc = cc_launch_matvec(dev, w->buf, dev->act_scratch, xf, (float*)c->base, m, k, b);
+    if (!rc && dev->exact) {
+        // exact_order: reference-layout activation blocks + scalar-order dot on the GGUF-layout weights
+        const uint8_t* wraw = cc_is_quant(wt) ? w->buf->raw : w->buf->plane[0];
+        if (!wraw) rc = cc_fail(dev, CC_ERR_TENSOR, "matmul_vec(exact): weight has no GGUF-layout copy");
+        void* blocks = nullptr; size_t cls = 0;
+        if (!rc && (at == CC_Q8_0 || at == CC_Q8_1 || at == CC_Q8_K)) {
+            rc = cc_pool_alloc(dev, (size_t)(b * k / cc_block_elems(at)) * cc_block_bytes(at), &blocks, &cls);
+            if (!rc) rc = cc_launch_act_to_blocks(dev, dev->act_scratch, b * k, at, (uint8_t*)blocks);
+        }
+        const uint8_t* act = blocks ? (const uint8_t*)blocks : at == CC_F32 ? (const uint8_t*)xf : (const uint8_t*)dev->act_scratch;
+        if (!rc) rc = cc_launch_matvec_exact(dev, wt, wraw, act, (float*)c->base, m, k, b);
+        if (blocks) cc_pool_free(dev, blocks, cls);
+    } else if (!rc) rc = cc_launch_matvec(dev, w->buf, dev->act_scratch, xf, (float*)c->base, m, k, b);
     if (rc) { cc_tensor_release(c); return rc; }
     *out = c;
     return CC_OK;
@@ -248,8 +264,12 @@ extern "C" CC_API int cc_batch_matmul(cc_device* dev, const cc_view* a, const cc
     cc_buf* c = nullptr;
     int rc = cc_new_activation(dev, ab * m * n, CC_F32, false, &c);
     if (rc) return rc;
-    rc = cc_launch_batch_matmul(dev, (const float*)a->buf->plane[0], b->buf->plane[0], bt, (float*)c->base, ab, bb, m, k, n,
-                                b->strides[0], b->strides[1], b->strides[2]);
+    if (dev->exact && b->strides[1] == 1)
+        rc = cc_launch_bmm_kcontig_exact(dev, (const float*)a->buf->plane[0], b->buf->plane[0], bt, (float*)c->base, ab, bb, m, k, n,
+                                         b->strides[0], b->strides[2]);
+    else
+        rc = cc_launch_batch_matmul(dev, (const float*)a->buf->plane[0], b->buf->plane[0], bt, (float*)c->base, ab, bb, m, k, n,
+                                    b->strides[0], b->strides[1], b->strides[2]);
     if (rc) { cc_tensor_release(c); return rc; }
     *out = c;
     return CC_OK;

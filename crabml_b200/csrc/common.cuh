@@ -50,6 +50,7 @@ struct cc_buf {
     bool pooled = false;       // came from the activation pool (size class = bytes)
     int64_t rows = 0, cols = 0;  // quantized matrices
     uint8_t* plane[CC_MAX_PLANES] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t* raw = nullptr;    // GGUF-layout copy, kept only on exact_order devices (exact.cu)
 };
 
 // On-device activation formats: what buf/api.rs:195-228 `quantize` produces, as SoA.
@@ -73,6 +74,7 @@ struct cc_device {
     cudaStream_t stream = nullptr;
     bool debug_named_tensors = false;
     bool lazy = false;
+    bool exact = false;       // cc_device_options.exact_order
     std::string last_error;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -159,8 +161,6 @@ int cc_launch_matvec(cc_device* dev, const cc_buf* w, const void* act_scratch, c
 
 // ---- ops.cu --------------------------------------------------------------------------------------
 int cc_launch_rms_norm(cc_device* dev, float* x, int64_t rows, int64_t cols, float eps);
-int cc_launch_rope(cc_device* dev, float* x, int64_t n_batch, int64_t batch_stride, int64_t head_dim,
-                   int mode, int64_t pos, int64_t rope_dim);
 int cc_launch_softmax(cc_device* dev, float* x, int64_t rows, int64_t cols);
 int cc_launch_silu(cc_device* dev, float* x, int64_t n);
 int cc_launch_gelu(cc_device* dev, float* x, int64_t n);
@@ -172,6 +172,16 @@ int cc_launch_strided_copy(cc_device* dev, const void* src, int src_dtype, const
 int cc_launch_batch_matmul(cc_device* dev, const float* a, const void* b, int b_dtype, float* c,
                            int64_t a_batch, int64_t b_batch, int64_t m, int64_t k, int64_t n,
                            int64_t sb0, int64_t sb1, int64_t sb2);
+
+// ---- exact.cu (exact_order verification mode) -------------------------------------------------------
+int cc_launch_matvec_exact(cc_device* dev, int t, const uint8_t* w_gguf, const uint8_t* act_blocks, float* out,
+                           int64_t m, int64_t k, int64_t b);
+int cc_launch_rms_norm_exact(cc_device* dev, float* x, int64_t rows, int64_t cols, float eps);
+int cc_launch_softmax_exact(cc_device* dev, float* x, int64_t rows, int64_t cols);
+int cc_launch_rope_exact(cc_device* dev, float* x, int64_t n_batch, int64_t batch_stride, int64_t head_dim, int mode,
+                         int64_t pos, int64_t rope_dim);
+int cc_launch_bmm_kcontig_exact(cc_device* dev, const float* a, const void* b, int b_dtype, float* c, int64_t ab, int64_t bb,
+                                int64_t m, int64_t k, int64_t n, int64_t sb0, int64_t sb2);
 
 // ---- small device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__

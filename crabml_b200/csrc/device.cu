@@ -71,6 +71,7 @@ extern "C" CC_API int cc_device_create(const cc_device_options* opts, cc_device*
     dev->ordinal = ord;
     dev->debug_named_tensors = opts && opts->debug_named_tensors;
     dev->lazy = opts && opts->lazy;
+    dev->exact = opts && opts->exact_order;
 #define CREATE_CUDA(call)                                                                          \
     do { cudaError_t _e = (call); if (_e != cudaSuccess) { cc_fail(nullptr, CC_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); delete dev; return CC_ERR_CUDA; } } while (0)
     CREATE_CUDA(cudaSetDevice(ord));
@@ -191,6 +192,7 @@ extern "C" CC_API void cc_tensor_release(cc_buf* b) {
     if (b->refs.fetch_sub(1) != 1) return;
     if (b->pooled) cc_pool_free(b->dev, b->base, b->bytes);
     else if (b->base) { cudaSetDevice(b->dev->ordinal); cudaFree(b->base); }
+    if (b->raw) cudaFree(b->raw);
     delete b;
 }
 extern "C" CC_API int32_t cc_tensor_dtype(const cc_buf* b) { return b ? b->dtype : -1; }
@@ -247,9 +249,9 @@ extern "C" CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size
     cc_assign_planes(b);
     int rc = cc_launch_repack(dev, staging, b);
     cudaError_t e2 = cudaStreamSynchronize(dev->stream);
-    cudaFree(staging);
+    if (dev->exact) b->raw = staging; else cudaFree(staging);     // exact_order keeps the GGUF-layout bytes
     if (rc == CC_OK && e2 != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "repack: %s", cudaGetErrorString(e2));
-    if (rc != CC_OK) { cudaFree(b->base); delete b; return rc; }
+    if (rc != CC_OK) { cudaFree(b->base); if (b->raw) cudaFree(b->raw); delete b; return rc; }
     *out = b;
     return CC_OK;
 }

@@ -48,47 +48,7 @@ int cc_launch_rms_norm(cc_device* dev, float* x, int64_t rows, int64_t cols, flo
     return CC_OK;
 }
 
-// ---- rope_inplace: primitives/rope.rs:47-80 ----------------------------------------------------------------
-// Llama mode: pairs (i, i+1); theta_0 = pos, theta_{j+1} = theta_j * theta_scale evaluated as the SAME f32
-// recurrence as the reference (quirk B6), theta_scale = powf(10000, -2/head_dim) computed on the host.
-__global__ void rope_kernel(float* x, int64_t n_batch, int64_t batch_stride, int head_dim, int mode, int64_t pos,
-                            int rope_dim, float theta_scale) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int pairs = rope_dim / 2;
-    int64_t heads = batch_stride / head_dim;
-    int64_t total = n_batch * heads * pairs;
-    if (idx >= total) return;
-    int j = (int)(idx % pairs);
-    int64_t h = (idx / pairs) % heads, bi = idx / (pairs * heads);
-    float* c = x + bi * batch_stride + h * head_dim;
-    float fpos = (float)(pos + bi);                          // rope.rs:36
-    if (mode == CC_ROPE_LLAMA) {
-        float theta = fpos;
-        for (int t = 0; t < j; t++) theta *= theta_scale;
-        float ct = cosf(theta), st = sinf(theta);
-        float q0 = c[2 * j], q1 = c[2 * j + 1];
-        c[2 * j] = q0 * ct - q1 * st;
-        c[2 * j + 1] = q0 * st + q1 * ct;
-    } else {                                                 // Neox: pairs (i, i + head_dim/2), closed form powf
-        float fe = 2.0f * (float)j / (float)head_dim;
-        float timescale = powf(10000.0f, fe);
-        float theta = fpos / timescale;
-        float ct = cosf(theta), st = sinf(theta);
-        float q0 = c[j], q1 = c[j + head_dim / 2];
-        c[j] = q0 * ct - q1 * st;
-        c[j + head_dim / 2] = q0 * st + q1 * ct;
-    }
-}
-int cc_launch_rope(cc_device* dev, float* x, int64_t n_batch, int64_t batch_stride, int64_t head_dim, int mode,
-                   int64_t pos, int64_t rope_dim) {
-    int64_t total = n_batch * (batch_stride / head_dim) * (rope_dim / 2);
-    if (total == 0) return CC_OK;
-    float theta_scale = powf(10000.0f, -2.0f / (float)head_dim);     // host libm, like the reference
-    rope_kernel<<<(unsigned)((total + 127) / 128), 128, 0, dev->stream>>>(x, n_batch, batch_stride, (int)head_dim, mode, pos,
-                                                                          (int)rope_dim, theta_scale);
-    CC_LAUNCH_CHECK(dev);
-    return CC_OK;
-}
+// rope_inplace lives in exact.cu (host-evaluated cos/sin table, used by both modes)
 
 // ---- softmax_inplace: primitives/softmax.rs:39-54 with the f16 exp LUT (quirk B4) ---------------------------
 __device__ __forceinline__ float exp_cached(float v, const uint16_t* lut) { return h2f_bits(lut[f2h_bits(v)]); }

@@ -167,14 +167,14 @@ __global__ void act_to_blocks_kernel(int t, const void* scratch, int64_t n, uint
     if (t == CC_Q8_0) {
         if (b >= n / 32) return;
         uint8_t* o = out + b * 34;
-        uint16_t h = f2h_bits(a0.d[b]);
-        o[0] = h & 0xFF; o[1] = h >> 8;
+        // 16-bit store on purpose: ptxas 12.9 folds `cvt.rn.f16.f32` + a truncating byte store into a
+        // NUMERIC F2I.U8.F16 (observed on sm_100a), so never narrow f16 bits with `& 0xFF`.
+        *reinterpret_cast<__half*>(o) = __float2half_rn(a0.d[b]);
         for (int i = 0; i < 32; i++) o[2 + i] = (uint8_t)a0.qs[b * 32 + i];
     } else if (t == CC_Q8_1) {
         if (b >= n / 32) return;
         uint8_t* o = out + b * 36;
-        uint16_t hd = __half_as_ushort(__low2half(a1.ds[b])), hs = __half_as_ushort(__high2half(a1.ds[b]));
-        o[0] = hd & 0xFF; o[1] = hd >> 8; o[2] = hs & 0xFF; o[3] = hs >> 8;
+        *reinterpret_cast<__half2*>(o) = a1.ds[b];
         for (int i = 0; i < 32; i++) o[4 + i] = (uint8_t)a1.qs[b * 32 + i];
     } else {
         if (b >= n / 256) return;

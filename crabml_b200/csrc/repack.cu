@@ -292,9 +292,9 @@ __global__ void synth_scales_kernel(uint8_t* out, int64_t nblocks, int bb, Synth
         float u = (float)((r >> (16 * f)) & 0xFFFF) * (1.0f / 65536.0f);
         float v = scale * exp2f(u - 0.5f);
         if (sp.is_min[f]) v *= 0.25f;
-        uint16_t h = f2h_bits(v);
-        out[b * bb + sp.off[f]] = (uint8_t)(h & 0xFF);
-        out[b * bb + sp.off[f] + 1] = (uint8_t)(h >> 8);
+        // 16-bit store (all f16 fields sit at even offsets of even-sized blocks); see quantize.cu on why
+        // f16 bits must not be narrowed bytewise
+        *reinterpret_cast<__half*>(out + b * bb + sp.off[f]) = __float2half_rn(v);
     }
     if (sp.d_f32_off >= 0) {
         float u = (float)(r & 0xFFFF) * (1.0f / 65536.0f);

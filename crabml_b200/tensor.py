@@ -69,9 +69,9 @@ class TensorStrider:
 class CudaTensorDevice:
     """T::DeviceRef.  Options mirror CpuTensorDeviceOptions (cpu_device.rs:13-48)."""
 
-    def __init__(self, ordinal=0, debug_named_tensors=False, lazy=False):
+    def __init__(self, ordinal=0, debug_named_tensors=False, lazy=False, exact_order=False):
         self.lib = capi.load_library()
-        opts = capi.cc_device_options(ordinal, int(debug_named_tensors), int(lazy), 0, 0)
+        opts = capi.cc_device_options(ordinal, int(debug_named_tensors), int(lazy), int(exact_order), 0)
         h = C.c_void_p()
         rc = self.lib.cc_device_create(C.byref(opts), C.byref(h))
         if rc != capi.CC_OK:

@@ -102,3 +102,20 @@ def test_truncation_vs_rounding_is_visible(gdev):
     w = oc.dequantize(oc.Q8_0, raw, m * k).reshape(m, k)
     rounded = w @ (q_round * d.astype(np.float16).astype(np.float32)).reshape(-1)
     assert np.abs(rounded - want).max() > 50 * np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("t", oc.QUANT_TYPES)
+def test_matvec_exact_order_bit_identical(t):
+    """exact_order mode: the scalar reference order (buf_q*.rs vec_dot_*_fallback) -> bit-identical rows."""
+    from crabml_b200 import CudaTensor
+    dev = make_device(exact_order=True)
+    try:
+        rng = np.random.default_rng(500 + t)
+        for (m, k) in ((19, 512), (5, 4096)):
+            raw = random_weight(t, m, k, rng)
+            x = rng.standard_normal(k).astype(np.float32)
+            got = CudaTensor.from_cpu(raw, [m, k], t, dev).matmul_vec(CudaTensor.new(x, [k], dev)).export()
+            want = oc.gemv(t, raw, m, k, x)
+            np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32), err_msg=oc.TYPE_NAMES[t])
+    finally:
+        dev.close()

@@ -61,7 +61,8 @@ def test_rope_vs_oracle(gdev, odev, mode, shape, pos, rope_dim):
     rng = np.random.default_rng(5)
     g, o = both(rng.standard_normal(int(np.prod(shape))), shape, gdev, odev)
     # cosf/sinf differ from glibc by <= 2 ulp: tolerance 1e-5 abs like the reference KAT
-    np.testing.assert_allclose(g.rope_inplace(mode, pos, rope_dim).export(), o.rope_inplace(mode, pos, rope_dim).export(), atol=2e-6, rtol=2e-6)
+    # cos/sin come from the host libm (same calls as the reference): bit-exact
+    np.testing.assert_array_equal(g.rope_inplace(mode, pos, rope_dim).export().view(np.uint32), o.rope_inplace(mode, pos, rope_dim).export().view(np.uint32))
 
 
 def test_matmul_f32_kats(gdev):
@@ -90,7 +91,8 @@ def test_softmax_vs_oracle(gdev, odev, shape):
     rng = np.random.default_rng(6)
     g, o = both(rng.standard_normal(int(np.prod(shape))) * 4, shape, gdev, odev)
     ax = len(shape) - 1
-    np.testing.assert_allclose(g.softmax_inplace(ax).export(), o.softmax_inplace(ax).export(), rtol=1e-6, atol=0)
+    # identical LUT exps; only the order of the f32 sum differs (tree vs sequential)
+    np.testing.assert_allclose(g.softmax_inplace(ax).export(), o.softmax_inplace(ax).export(), rtol=5e-6, atol=0)
 
 
 def test_silu_gelu_bit_exact(gdev, odev):
@@ -191,7 +193,11 @@ def test_batch_matmul_attention_shapes(gdev, odev, kv_dtype, heads, kv_heads, hd
     g_att = gq.batch_matmul(gk.transpose([0, 2, 1]))
     o_att = oq.batch_matmul(ok.transpose([0, 2, 1]))
     assert g_att.shape() == [heads, 1, seq]
-    np.testing.assert_allclose(g_att.export(), o_att.export(), rtol=3e-6, atol=3e-6)
+    # f32 summation-order noise, budgeted against sum |q_i k_i| per output
+    kk = rows.transpose(1, 0, 2)                                  # [kv, seq, hd]
+    grp = (np.arange(heads) % kv_heads) if kv_dtype == oc.F32 else (np.arange(heads) // (heads // kv_heads))
+    budget = np.einsum("hd,hsd->hs", np.abs(q.reshape(heads, hd)), np.abs(kk[grp])) * 1e-6 + 1e-7
+    assert (np.abs(g_att.export() - o_att.export()).reshape(heads, seq) <= budget).all()
     # PV with identical attention weights on both sides
     w = np.abs(rng.standard_normal(heads * seq)).astype(np.float32)
     gw, ow = both(w, [heads, 1, seq], gdev, odev)
