@@ -15,9 +15,12 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-3      # north_star bar (relative to max |logit|); met -- with equality -- in exact_order mode
 
 
-def _band(path):
+def _band():
+    # the q4_0 fixture has 9 blocks/row, where the reference's Q4_0 AVX2 kernel falls back to the scalar loop
+    # (buf_q4_0.rs:220-223), so the band is taken on the q8_0 twin of the same model
+    from tests.conftest import find_fixture
     from tests.test_oracle_order_sensitivity import order_band
-    return float(order_band(path)[0].max())
+    return float(order_band(find_fixture("tinyllamas-stories-15m-q8_0.gguf"))[0].max())
 
 
 def _run(T, dev, gm, steps, f16_kv=False):
@@ -77,7 +80,7 @@ def test_fast_mode_generation_and_band(fixture_path, fname, text, ids):
         o_out, o_logits = _run(OracleTensor, odev, gm, 11)
         assert g_out == o_out == ids and decode_text(tok, g_out) == text
         rel = (np.abs(g_logits - o_logits) / np.abs(o_logits).max(axis=1, keepdims=True)).max()
-        band = _band(path)
+        band = _band()
         print(f"{fname}: fast-mode max rel logits diff {rel:.3e}; reference scalar-vs-AVX2 band {band:.3e}")
         assert rel <= 1.5 * band, (rel, band)
         # before any re-quantisation of perturbed values the agreement is at f32 rounding level
