@@ -8,6 +8,7 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libcrabml_cuda.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "crabml_cuda.h")
+RUNNER_HEADER = os.path.join(os.path.dirname(HERE), "include", "crabml_runner.h")
 
 CC_OK, CC_ERR_TENSOR, CC_ERR_CUDA, CC_ERR_ARG, CC_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 CC_MAX_DIMS = 4
@@ -36,9 +37,24 @@ class cc_device_options(C.Structure):
 
 
 def declared_symbols():
-    """Every CC_API prototype name in the header (used by the CPU-side export test)."""
-    with open(HEADER) as f:
-        return re.findall(r"^CC_API [\w\s\*]+?\b(cc\w*)\(", f.read(), flags=re.M)
+    """Every CC_API prototype name in the headers (used by the CPU-side export test)."""
+    out = []
+    for h in (HEADER, RUNNER_HEADER):
+        with open(h) as f:
+            out += re.findall(r"^CC_API [\w\s\*]+?\b(ccr?_\w*)\(", f.read(), flags=re.M)
+    return out
+
+
+class ccr_llama_config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_heads", "n_kv_heads", "n_layers", "embedding_dim", "hidden_dim", "seq_len", "vocab_size", "rope_dim")] + \
+               [("rms_norm_eps", C.c_float), ("use_f16_kv_cache", C.c_int32)]
+
+
+class ccr_llama_weights(C.Structure):
+    _pp = C.POINTER(C.c_void_p)
+    _fields_ = [("token_embed", C.c_void_p), ("wq", _pp), ("wk", _pp), ("wv", _pp), ("wo", _pp), ("ffn_gate", _pp),
+                ("ffn_down", _pp), ("ffn_up", _pp), ("rms_att", _pp), ("rms_ffn", _pp), ("rms_final", C.c_void_p),
+                ("output_weight", C.c_void_p)]
 
 
 _lib = None
@@ -92,7 +108,17 @@ def load_library(build_if_missing: bool = True):
         "cc_test_quantize_activation": (i32, [vp, pv, i32, vp, sz]),
         "cc_tensor_synth": (i32, [vp, C.POINTER(i64), i32, i32, u64, u64, f32, pp]),
         "cc_test_export_blocks": (i32, [vp, vp, vp, sz]),
+        "cc_bench_timer_begin": (i32, [vp]),
+        "cc_bench_timer_end": (i32, [vp, C.POINTER(f32)]),
     }
+    sig.update({
+        "ccr_runner_create": (i32, [vp, C.POINTER(ccr_llama_config), C.POINTER(ccr_llama_weights), i32, pp]),
+        "ccr_runner_destroy": (None, [vp]),
+        "ccr_runner_last_error": (C.c_char_p, [vp]),
+        "ccr_runner_forward": (i32, [vp, C.POINTER(i64), i32, i64, vp]),
+        "ccr_runner_kv_cache_len": (i64, [vp]),
+        "ccr_runner_generate_greedy": (i32, [vp, C.POINTER(i64), i32, i32, i64, C.POINTER(i64), C.POINTER(i32)]),
+    })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args

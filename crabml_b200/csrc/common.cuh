@@ -98,6 +98,8 @@ struct cc_device {
     void* dev_idx = nullptr;      // device copy of row indices
     size_t dev_idx_bytes = 0;
 
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;    // cc_bench_timer_*
+
     // debug tap
     std::map<std::string, std::vector<float>> debug_tensors;
 };

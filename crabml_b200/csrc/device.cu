@@ -116,6 +116,20 @@ extern "C" CC_API int cc_device_synchronize(cc_device* dev) {
     return CC_OK;
 }
 
+extern "C" CC_API int cc_bench_timer_begin(cc_device* dev) {
+    if (!dev) return CC_ERR_ARG;
+    if (!dev->ev_begin) { CC_CUDA(dev, cudaEventCreate(&dev->ev_begin)); CC_CUDA(dev, cudaEventCreate(&dev->ev_end)); }
+    CC_CUDA(dev, cudaEventRecord(dev->ev_begin, dev->stream));
+    return CC_OK;
+}
+extern "C" CC_API int cc_bench_timer_end(cc_device* dev, float* ms) {
+    if (!dev || !ms || !dev->ev_begin) return CC_ERR_ARG;
+    CC_CUDA(dev, cudaEventRecord(dev->ev_end, dev->stream));
+    CC_CUDA(dev, cudaEventSynchronize(dev->ev_end));
+    CC_CUDA(dev, cudaEventElapsedTime(ms, dev->ev_begin, dev->ev_end));
+    return CC_OK;
+}
+
 // ---- activation pool: power-of-two size classes, stream-ordered reuse (single stream) -------------
 static size_t size_class(size_t bytes) {
     size_t c = 512;

@@ -1,0 +1,206 @@
+// llama2_runner.cpp -- replay of crabml-llama2's Llama2Runner<T> with T = CudaTensor.
+// The op ORDER is the reference's, verbatim (llama2.rs:184-281 forward/forward_llama, :527-603 attention,
+// :605-638 ffn); this file contains no arithmetic of its own.
+#include <cmath>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/crabml_runner.h"
+#include "cuda_tensor.hpp"
+
+using crabml::CudaTensor;
+using crabml::TensorStrider;
+
+struct ccr_runner {
+    cc_device* dev = nullptr;
+    ccr_llama_config conf{};
+    CudaTensor token_embed, rms_final, output_weight;
+    std::vector<CudaTensor> wq, wk, wv, wo, ffn_gate, ffn_down, ffn_up, rms_att, rms_ffn;
+    std::vector<CudaTensor> key_cache, value_cache;       // (layer) x [n_kv_heads, seq, head_dim]
+    std::vector<float> logits;
+    std::string last_error;
+
+    int head_size() const { return conf.embedding_dim / conf.n_heads; }
+    int64_t kv_cache_len() const { return key_cache[0].shape()[1]; }
+
+    CudaTensor forward_llama(const std::vector<int64_t>& tokens, int64_t pos);
+    CudaTensor forward_multi_query_attention(CudaTensor q, CudaTensor k, CudaTensor v, int l, int64_t n_batch);
+    CudaTensor forward_ffn(CudaTensor x, int l);
+    void forward(const std::vector<int64_t>& tokens, int64_t pos, float* logits_out);
+};
+
+// llama2.rs:184-211
+void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float* logits_out) {
+    CudaTensor x = forward_llama(tokens, pos);
+    CudaTensor x_final = CudaTensor::alloc({conf.embedding_dim}, CC_F32, dev);
+    x_final.copy_rows_from(x, {(int64_t)tokens.size() - 1});
+    const CudaTensor& ow = output_weight.valid() ? output_weight : token_embed;
+    CudaTensor lg = ow.matmul_vec(x_final);
+    if (logits_out) lg.export_to(logits_out, (size_t)conf.vocab_size);
+}
+
+// llama2.rs:213-281
+CudaTensor ccr_runner::forward_llama(const std::vector<int64_t>& tokens, int64_t pos) {
+    const int64_t embed_dim = conf.embedding_dim, n_heads = conf.n_heads, n_kv_heads = conf.n_kv_heads;
+    const int64_t head_dim = head_size();
+    const int64_t rope_dim = conf.rope_dim > 0 ? conf.rope_dim : head_dim;
+    const int64_t n_batch = (int64_t)tokens.size();
+
+    CudaTensor x = CudaTensor::alloc({n_batch, embed_dim}, CC_F32, dev);
+    x.copy_rows_from(token_embed, tokens);
+
+    for (int l = 0; l < conf.n_layers; l++) {
+        CudaTensor x_attn_orig = x.dup();
+        x = std::move(x).rms_norm_inplace(conf.rms_norm_eps);
+        x = std::move(x).mul_inplace(rms_att[l]);
+        x = std::move(x).with_name("attn_rmsnorm:" + std::to_string(l) + ":" + std::to_string(pos));
+        x = std::move(x).with_name("x_debug:" + std::to_string(l) + ":" + std::to_string(pos));
+
+        CudaTensor q = wq[l].matmul_vec(x);
+        CudaTensor k = wk[l].matmul_vec(x);
+        CudaTensor v = wv[l].matmul_vec(x);
+
+        q = std::move(q).reshape({n_batch, n_heads, head_dim});
+        k = std::move(k).reshape({n_batch, n_kv_heads, head_dim});
+        q = std::move(q).rope_inplace(CC_ROPE_LLAMA, pos, rope_dim);
+        k = std::move(k).rope_inplace(CC_ROPE_LLAMA, pos, rope_dim);
+
+        x = forward_multi_query_attention(std::move(q), std::move(k), std::move(v), l, n_batch);
+        x = std::move(x).with_name("attn_out:" + std::to_string(l) + ":" + std::to_string(pos));
+        x = std::move(x).add_inplace(x_attn_orig);
+        x = forward_ffn(std::move(x), l);
+        x = std::move(x).with_name("ffn_out:" + std::to_string(l) + ":" + std::to_string(pos));
+    }
+    x = std::move(x).rms_norm_inplace(conf.rms_norm_eps);
+    x = std::move(x).mul_inplace(rms_final);
+    return std::move(x).with_name("final_rmsnorm:" + std::to_string(pos));
+}
+
+// llama2.rs:527-603
+CudaTensor ccr_runner::forward_multi_query_attention(CudaTensor q, CudaTensor k, CudaTensor v, int l, int64_t n_batch) {
+    const int64_t n_heads = conf.n_heads, n_kv_heads = conf.n_kv_heads, head_dim = head_size(), embed_dim = conf.embedding_dim;
+    {
+        CudaTensor kt = std::move(k).reshape({n_batch, n_kv_heads, head_dim}).transpose({1, 0, 2});
+        CudaTensor vt = std::move(v).reshape({n_batch, n_kv_heads, head_dim}).transpose({1, 0, 2});
+        key_cache[l].concatenate(kt, 1);
+        value_cache[l].concatenate(vt, 1);
+    }
+    q = std::move(q).reshape({n_batch, n_heads, head_dim}).transpose({1, 0, 2}).contiguous().scale_inplace(1.0f / std::sqrt((float)head_dim));
+
+    CudaTensor k_cache = std::move(key_cache[l]);
+    TensorStrider k_strider_orig = k_cache.strider();
+    k_cache = std::move(k_cache).transpose({0, 2, 1});
+    CudaTensor attn = q.batch_matmul(k_cache);
+    attn = std::move(attn).softmax_inplace(2);
+    key_cache[l] = std::move(k_cache).with_strider(k_strider_orig);
+
+    CudaTensor v_cache = std::move(value_cache[l]);
+    TensorStrider v_strider_orig = v_cache.strider();
+    CudaTensor x_with_attn = attn.batch_matmul(v_cache);
+    if (n_batch == 1) x_with_attn = std::move(x_with_attn).reshape({n_batch, embed_dim});
+    else x_with_attn = std::move(x_with_attn).transpose({1, 0, 2}).contiguous().reshape({n_batch, embed_dim});
+    value_cache[l] = std::move(v_cache).with_strider(v_strider_orig);
+    return wo[l].matmul_vec(x_with_attn);
+}
+
+// llama2.rs:605-638
+CudaTensor ccr_runner::forward_ffn(CudaTensor x, int l) {
+    CudaTensor x_orig_ffn = x.dup();
+    x = std::move(x).rms_norm_inplace(1e-5f);              // literal in the reference (quirk B5)
+    x = std::move(x).mul_inplace(rms_ffn[l]);
+    CudaTensor h1 = ffn_gate[l].matmul_vec(x);
+    CudaTensor h2 = ffn_up[l].matmul_vec(x);
+    h1 = std::move(h1).silu_inplace();
+    h1 = std::move(h1).mul_inplace(h2);
+    x = ffn_down[l].matmul_vec(h1);
+    x = std::move(x).add_inplace(x_orig_ffn);
+    return x;
+}
+
+static int64_t sample_argmax(const std::vector<float>& logits) {       // sampler.rs:109-116: max_by keeps the LAST maximum
+    int64_t best = 0;
+    for (int64_t i = 1; i < (int64_t)logits.size(); i++)
+        if (!(logits[i] < logits[best])) best = i;
+    return best;
+}
+
+template <class F>
+static int guarded(ccr_runner* r, F&& f) {
+    try {
+        f();
+        return CC_OK;
+    } catch (const crabml::TensorError& e) {
+        if (r) r->last_error = e.what();
+        return CC_ERR_TENSOR;
+    } catch (const std::exception& e) {
+        if (r) r->last_error = e.what();
+        return CC_ERR_ARG;
+    }
+}
+
+extern "C" CC_API int ccr_runner_create(cc_device* dev, const ccr_llama_config* conf, const ccr_llama_weights* w,
+                                        int32_t kv_seq_len, ccr_runner** out) {
+    if (!dev || !conf || !w || !out) return CC_ERR_ARG;
+    ccr_runner* r = new ccr_runner();
+    r->dev = dev;
+    r->conf = *conf;
+    int rc = guarded(r, [&] {
+        const int64_t dim = conf->embedding_dim, hidden = conf->hidden_dim, hd = dim / conf->n_heads, kv_dim = hd * conf->n_kv_heads;
+        r->token_embed = CudaTensor::wrap(dev, w->token_embed, {conf->vocab_size, dim});
+        r->rms_final = CudaTensor::wrap(dev, w->rms_final, {dim});
+        if (w->output_weight) r->output_weight = CudaTensor::wrap(dev, w->output_weight, {conf->vocab_size, dim});
+        for (int l = 0; l < conf->n_layers; l++) {
+            r->wq.push_back(CudaTensor::wrap(dev, w->wq[l], {dim, dim}));
+            r->wk.push_back(CudaTensor::wrap(dev, w->wk[l], {kv_dim, dim}));
+            r->wv.push_back(CudaTensor::wrap(dev, w->wv[l], {kv_dim, dim}));
+            r->wo.push_back(CudaTensor::wrap(dev, w->wo[l], {dim, dim}));
+            r->ffn_gate.push_back(CudaTensor::wrap(dev, w->ffn_gate[l], {hidden, dim}));
+            r->ffn_down.push_back(CudaTensor::wrap(dev, w->ffn_down[l], {dim, hidden}));
+            r->ffn_up.push_back(CudaTensor::wrap(dev, w->ffn_up[l], {hidden, dim}));
+            r->rms_att.push_back(CudaTensor::wrap(dev, w->rms_att[l], {dim}));
+            r->rms_ffn.push_back(CudaTensor::wrap(dev, w->rms_ffn[l], {dim}));
+            // llama2.rs:65-86: pre-allocated [n_kv_heads, seq_len, head_dim], resized to length 0
+            int kvt = conf->use_f16_kv_cache ? CC_F16 : CC_F32;
+            r->key_cache.push_back(CudaTensor::alloc({conf->n_kv_heads, kv_seq_len, hd}, kvt, dev).resize(1, 0));
+            r->value_cache.push_back(CudaTensor::alloc({conf->n_kv_heads, kv_seq_len, hd}, kvt, dev).resize(1, 0));
+        }
+        r->logits.assign((size_t)conf->vocab_size, 0.0f);
+    });
+    if (rc != CC_OK) { delete r; return rc; }
+    *out = r;
+    return CC_OK;
+}
+
+extern "C" CC_API void ccr_runner_destroy(ccr_runner* r) { delete r; }
+extern "C" CC_API const char* ccr_runner_last_error(ccr_runner* r) { return r ? r->last_error.c_str() : ""; }
+extern "C" CC_API int64_t ccr_runner_kv_cache_len(ccr_runner* r) { return r ? r->kv_cache_len() : -1; }
+
+extern "C" CC_API int ccr_runner_forward(ccr_runner* r, const int64_t* tokens, int32_t n_tokens, int64_t pos, float* logits_out) {
+    if (!r || !tokens || n_tokens < 1) return CC_ERR_ARG;
+    return guarded(r, [&] { r->forward(std::vector<int64_t>(tokens, tokens + n_tokens), pos, logits_out); });
+}
+
+extern "C" CC_API int ccr_runner_generate_greedy(ccr_runner* r, const int64_t* prompt, int32_t n_prompt, int32_t steps,
+                                                 int64_t eos_token, int64_t* out_tokens, int32_t* n_out) {
+    if (!r || !prompt || n_prompt < 1 || !out_tokens || !n_out) return CC_ERR_ARG;
+    *n_out = 0;
+    return guarded(r, [&] {
+        // prefill: one forward per prompt token (llama2.rs:127-129), then sample
+        int64_t base_pos = r->kv_cache_len();
+        for (int i = 0; i < n_prompt; i++) r->forward({prompt[i]}, base_pos + i, r->logits.data());
+        int64_t token = sample_argmax(r->logits);
+        int64_t pos = r->kv_cache_len();
+        // generate (llama2.rs:141-172): the first token comes from prefill
+        int64_t max_seq = r->conf.seq_len - pos - 1;
+        int64_t max_steps = std::min<int64_t>(max_seq, (int64_t)steps - 1);
+        out_tokens[(*n_out)++] = token;
+        for (int64_t p = pos; p < pos + max_steps; p++) {
+            r->forward({token}, p, r->logits.data());
+            int64_t nt = sample_argmax(r->logits);
+            if (nt == eos_token) return;
+            token = nt;
+            out_tokens[(*n_out)++] = token;
+        }
+    });
+}

@@ -250,8 +250,8 @@ int cc_launch_dequant_rows(cc_device* dev, const cc_buf* src, const int64_t* row
 
 // ---------------------------------------------------------------------------------------------------
 // Synthetic weights: counter-based splitmix64 over (seed, tensor, byte index)
-// written in GGUF block layout, f16 scale fields overwritten with log-uniform one-octave-wide values.
-// tests/synth.py holds the identical CPU generator.
+// written in GGUF block layout, f16 scale fields overwritten with values uniform in [0.75,1.25)*scale.
+// oracle/synth.py holds the identical CPU generator (checked bit for bit in tests/test_gpu_synth.py).
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -288,9 +288,9 @@ __global__ void synth_scales_kernel(uint8_t* out, int64_t nblocks, int bb, Synth
     if (b >= nblocks) return;
     uint64_t r = splitmix64(key ^ 0xD1B54A32D192ED03ull ^ (uint64_t)b);
     for (int f = 0; f < sp.n_f16; f++) {
-        // log-uniform in [scale/sqrt2, scale*sqrt2): one octave wide; mins get a random sign
+        // uniform in [0.75, 1.25) * scale: plain f32 mul/add only, so oracle/synth.py reproduces it bit for bit
         float u = (float)((r >> (16 * f)) & 0xFFFF) * (1.0f / 65536.0f);
-        float v = scale * exp2f(u - 0.5f);
+        float v = scale * (0.75f + 0.5f * u);
         if (sp.is_min[f]) v *= 0.25f;
         // 16-bit store (all f16 fields sit at even offsets of even-sized blocks); see quantize.cu on why
         // f16 bits must not be narrowed bytewise
@@ -298,7 +298,7 @@ __global__ void synth_scales_kernel(uint8_t* out, int64_t nblocks, int bb, Synth
     }
     if (sp.d_f32_off >= 0) {
         float u = (float)(r & 0xFFFF) * (1.0f / 65536.0f);
-        float v = scale * exp2f(u - 0.5f);
+        float v = scale * (0.75f + 0.5f * u);
         uint32_t bits = __float_as_uint(v);
         for (int j = 0; j < 4; j++) out[b * bb + sp.d_f32_off + j] = (uint8_t)(bits >> (8 * j));
     }

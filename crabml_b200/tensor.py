@@ -88,6 +88,13 @@ class CudaTensorDevice:
         raise CudaError(f"[{rc}] {msg}")
 
     def synchronize(self): self.check(self.lib.cc_device_synchronize(self.handle))
+
+    def timer_begin(self): self.check(self.lib.cc_bench_timer_begin(self.handle))
+
+    def timer_end(self) -> float:
+        ms = C.c_float(0)
+        self.check(self.lib.cc_bench_timer_end(self.handle, C.byref(ms)))
+        return float(ms.value)
     def launch_count(self): return int(self.lib.cc_device_launch_count(self.handle))
 
     def dump_debug_tensor(self, name):                              # cpu_device.rs:96-98

@@ -138,6 +138,10 @@ CC_API int cc_test_quantize_activation(cc_device* dev, const cc_view* x, int32_t
  * RNG, identical bytes to tests/synth.py's CPU generator for the same (seed, tensor_id). */
 CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t ggml_type,
                     uint64_t seed, uint64_t tensor_id, float scale, cc_buf** out);
+/* CUDA-event timer on the device's stream (bench.py): begin records an event; end records, synchronises
+ * and returns the elapsed milliseconds between the two */
+CC_API int cc_bench_timer_begin(cc_device* dev);
+CC_API int cc_bench_timer_end(cc_device* dev, float* ms);
 /* copy a quantized tensor back in GGUF block layout (inverse of the load-time repack) */
 CC_API int cc_test_export_blocks(cc_device* dev, const cc_buf* buf, void* dst, size_t nbytes);
 

@@ -17,6 +17,7 @@
 #include <immintrin.h>
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -808,6 +809,45 @@ static void* gemv_worker(void* p) {
     return NULL;
 }
 
+/* thread_pool.rs:8-88: N persistent workers; `scoped` runs the first thunk on the caller, hands the others to
+ * the workers and busy-waits on a counter.  Restated with a generation counter + spin (then yield) waits. */
+#define OC_MAX_WORKERS 256
+static struct {
+    pthread_t tid[OC_MAX_WORKERS];
+    int n_workers;
+    gemv_job* jobs;              /* jobs[1..n_jobs-1] go to workers 0..n_jobs-2 */
+    int n_jobs;
+    volatile unsigned long gen;  /* bumped by the caller to publish a batch */
+    volatile int pending;        /* jobs not yet finished */
+    pthread_mutex_t mu;
+} g_pool = {.n_workers = 0, .mu = PTHREAD_MUTEX_INITIALIZER};
+
+static void* pool_worker(void* arg) {
+    long id = (long)arg;
+    unsigned long seen = 0;
+    for (;;) {
+        unsigned spins = 0;
+        while (__atomic_load_n(&g_pool.gen, __ATOMIC_ACQUIRE) == seen) {
+            if (++spins > 20000) { sched_yield(); if (spins > 40000) { usleep(200); } }
+        }
+        seen = __atomic_load_n(&g_pool.gen, __ATOMIC_ACQUIRE);
+        if (id + 1 < g_pool.n_jobs) {
+            gemv_worker(&g_pool.jobs[id + 1]);
+            __atomic_fetch_sub(&g_pool.pending, 1, __ATOMIC_ACQ_REL);
+        }
+    }
+    return NULL;
+}
+static void pool_ensure(int workers) {
+    if (workers > OC_MAX_WORKERS) workers = OC_MAX_WORKERS;
+    while (g_pool.n_workers < workers) {
+        long id = g_pool.n_workers;
+        pthread_create(&g_pool.tid[id], NULL, pool_worker, (void*)id);
+        pthread_detach(g_pool.tid[id]);
+        g_pool.n_workers++;
+    }
+}
+
 int oc_gemv_q(int w_type, const void* w, size_t m, size_t k, const void* act, size_t b,
               float* out, int threads, int flags) {
     int be = oc_block_elems(w_type);
@@ -821,19 +861,28 @@ int oc_gemv_q(int w_type, const void* w, size_t m, size_t k, const void* act, si
     if (work_len == 0) { work_len = len; }
     size_t nspans = (len + work_len - 1) / work_len;
     gemv_job* jobs = (gemv_job*)calloc(nspans, sizeof(gemv_job));
-    pthread_t* tids = (pthread_t*)calloc(nspans, sizeof(pthread_t));
     for (size_t s = 0; s < nspans; s++) {
         jobs[s] = (gemv_job){w_type, flags, (const uint8_t*)w, (const uint8_t*)act, m, k,
                              (k / (size_t)be) * oc_block_bytes(w_type),
                              (k / (size_t)oc_block_elems(at)) * oc_block_bytes(at),
                              out, s * work_len, (s + 1) * work_len < len ? (s + 1) * work_len : len};
     }
-    /* thread_pool.rs:38-70: first thunk inline, others on workers */
-    for (size_t s = 1; s < nspans; s++) pthread_create(&tids[s], NULL, gemv_worker, &jobs[s]);
-    gemv_worker(&jobs[0]);
-    for (size_t s = 1; s < nspans; s++) pthread_join(tids[s], NULL);
+    /* thread_pool.rs:38-70: first thunk inline, others on the pool's workers, busy-wait join */
+    if (nspans == 1 || nspans - 1 > OC_MAX_WORKERS) {
+        for (size_t s = 0; s < nspans; s++) gemv_worker(&jobs[s]);
+    } else {
+        pthread_mutex_lock(&g_pool.mu);
+        pool_ensure((int)nspans - 1);
+        g_pool.jobs = jobs;
+        g_pool.n_jobs = (int)nspans;
+        __atomic_store_n(&g_pool.pending, (int)nspans - 1, __ATOMIC_RELEASE);
+        __atomic_fetch_add(&g_pool.gen, 1, __ATOMIC_ACQ_REL);
+        gemv_worker(&jobs[0]);
+        while (__atomic_load_n(&g_pool.pending, __ATOMIC_ACQUIRE) > 0) { /* spin: thread_pool.rs:66-69 */ }
+        g_pool.n_jobs = 0;
+        pthread_mutex_unlock(&g_pool.mu);
+    }
     free(jobs);
-    free(tids);
     return 0;
 }
 
@@ -986,6 +1035,49 @@ void oc_batch_matmul_f16(const float* a, const uint16_t* b, float* c,
         free(tmp);
     }
     free(ah);
+}
+
+/* ------------------------------------------------------- synthetic weights -- */
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+int oc_synth_blocks(int t, size_t nblocks, uint64_t seed, uint64_t tid, float scale, void* outv) {
+    int n_f16 = 0, off[2] = {0, 0}, is_min[2] = {0, 0}, d32 = -1;
+    switch (t) {
+    case OC_Q8_0: case OC_Q4_0: case OC_Q5_0: n_f16 = 1; break;
+    case OC_Q4_1: case OC_Q5_1: case OC_Q4_K: case OC_Q5_K: n_f16 = 2; off[1] = 2; is_min[1] = 1; break;
+    case OC_Q2_K: n_f16 = 2; off[0] = 80; off[1] = 82; is_min[1] = 1; break;
+    case OC_Q3_K: n_f16 = 1; off[0] = 108; break;
+    case OC_Q6_K: n_f16 = 1; off[0] = 208; break;
+    case OC_Q8_K: d32 = 0; break;
+    default: return -1;
+    }
+    uint8_t* out = (uint8_t*)outv;
+    size_t bb = oc_block_bytes(t), total = nblocks * bb;
+    uint64_t key = splitmix64(seed ^ splitmix64(tid));
+    for (size_t w = 0; w * 8 < total; w++) {
+        uint64_t r = splitmix64(key ^ (uint64_t)w);
+        for (int j = 0; j < 8 && w * 8 + j < total; j++) out[w * 8 + j] = (uint8_t)(r >> (8 * j));
+    }
+    for (size_t b = 0; b < nblocks; b++) {
+        uint64_t r = splitmix64(key ^ 0xD1B54A32D192ED03ull ^ (uint64_t)b);
+        for (int f = 0; f < n_f16; f++) {
+            float u = (float)((r >> (16 * f)) & 0xFFFF) * (1.0f / 65536.0f);
+            float v = scale * (0.75f + 0.5f * u);
+            if (is_min[f]) v *= 0.25f;
+            uint16_t h = f2h(v);
+            memcpy(out + b * bb + off[f], &h, 2);
+        }
+        if (d32 >= 0) {
+            float u = (float)(r & 0xFFFF) * (1.0f / 65536.0f);
+            float v = scale * (0.75f + 0.5f * u);
+            memcpy(out + b * bb + d32, &v, 4);
+        }
+    }
+    return 0;
 }
 
 int oc_hw_threads(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }

@@ -74,6 +74,8 @@ void   oc_batch_matmul_f32(const float* a, const float* b, float* c,
 void   oc_batch_matmul_f16(const float* a, const uint16_t* b, float* c,
                            size_t a_batch, size_t b_batch, size_t m, size_t k, size_t n,
                            size_t sb0, size_t sb1, size_t sb2);
+/* CPU twin of the device synthetic-weight generator (crabml_b200/csrc/repack.cu); not reference code */
+int    oc_synth_blocks(int type, size_t nblocks, uint64_t seed, uint64_t tensor_id, float scale, void* out);
 /* hardware info used by bench.py */
 int    oc_hw_threads(void);
 

@@ -68,8 +68,19 @@ def lib():
         L.oc_batch_matmul_f32.argtypes = [vp, vp, vp] + [sz] * 8
         L.oc_batch_matmul_f16.argtypes = [vp, vp, vp] + [sz] * 8
         L.oc_hw_threads.restype = i32
+        L.oc_synth_blocks.argtypes = [i32, sz, C.c_uint64, C.c_uint64, f32, vp]; L.oc_synth_blocks.restype = i32
         _lib = L
     return _lib
+
+
+def big_empty(nbytes: int) -> np.ndarray:
+    """uint8 buffer backed by a pre-faulted anonymous mapping (MAP_POPULATE): first-touch page faults are very
+    slow in the sandbox VMs (~60 us each), which would dominate host-side weight generation."""
+    import mmap
+    if nbytes < (8 << 20):
+        return np.empty(nbytes, np.uint8)
+    m = mmap.mmap(-1, nbytes, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS | getattr(mmap, "MAP_POPULATE", 0x8000))
+    return np.frombuffer(m, np.uint8)
 
 
 def _p(a: np.ndarray):

@@ -1,0 +1,98 @@
+"""The C++ Llama2Runner replay (crabml_b200/csrc/host/llama2_runner.cpp, the product's host side) end to end:
+golden generations of the reference (llama2.rs:673-703), bit-identical logits in exact_order mode, and a
+Llama-2-7B-SHAPED layer on the synthetic weights bench.py uses (BASELINE.json configs 2-4 at full size)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as oc
+from oracle.llama_replay import GGUFModel, Llama2Runner, LlamaConfig as OConf, LlamaTokenizer, LlamaWeights, decode_text, load_weights
+from oracle.synth import synth_weight
+from oracle.tensor_ref import OracleDevice, OracleTensor
+from tests.gpu_common import make_device
+from tests.test_oracle_golden_text import CASES, PROMPT_IDS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("fname,text,ids", CASES)
+@pytest.mark.parametrize("exact", [False, True])
+def test_cpp_runner_golden_generation(fixture_path, fname, text, ids, exact):
+    from crabml_b200 import runner as R
+    path = fixture_path(fname)
+    dev = make_device(exact_order=exact)
+    try:
+        conf, w, tok = R.load_gguf(path, dev)
+        assert conf.rope_dim == 48 and conf.head_size() == 48
+        r = R.LlamaRunner(dev, conf, w, 200)
+        out = r.generate_greedy(PROMPT_IDS, 11, eos=tok["eos"])
+        assert out == ids
+        t = LlamaTokenizer(tok["tokens"], tok["scores"], tok["bos"], tok["eos"])
+        assert decode_text(t, out) == text
+        assert r.kv_cache_len() == len(PROMPT_IDS) + 10
+        r.close()
+    finally:
+        dev.close()
+
+
+@pytest.mark.parametrize("f16_kv", [False, True])
+def test_cpp_runner_exact_logits_bit_identical(fixture_path, f16_kv):
+    from crabml_b200 import runner as R
+    path = fixture_path("tinyllamas-stories-15m-q8_0.gguf")
+    gm = GGUFModel(path)
+    odev = OracleDevice()
+    ro = Llama2Runner(OracleTensor, gm.conf, load_weights(gm, OracleTensor, odev), odev, 64, use_f16_kv_cache=f16_kv)
+    dev = make_device(exact_order=True)
+    try:
+        conf, w, _ = R.load_gguf(path, dev)
+        r = R.LlamaRunner(dev, conf, w, 64, f16_kv=f16_kv)
+        for pos, t in enumerate(PROMPT_IDS + [29941, 2440]):
+            a = r.forward([t], pos).copy()
+            b = ro.forward([t], pos)
+            np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"pos {pos}")
+        r.close()
+    finally:
+        dev.close()
+
+
+@pytest.mark.parametrize("wt,ct", [(oc.Q8_0, oc.Q8_0), (oc.Q4_0, oc.Q6_K), (oc.Q4_K, oc.Q6_K)])
+def test_llama2_7b_shaped_layer_on_synthetic_weights(wt, ct):
+    """Full Llama-2-7B dimensions (4096 / 11008 / 32 heads / vocab 32000) with ONE layer: the synthetic weights
+    are generated on the device; the oracle runs on the bit-identical CPU twin.  exact_order -> equality;
+    fast mode -> within the order-noise budget of a single layer."""
+    from crabml_b200 import runner as R
+    conf = R.LlamaConfig(32, 32, 1, 4096, 11008, 4096, 32000, 1e-5, 128)
+    seed = 0x5EED
+    odev = OracleDevice()
+    dim, hid = conf.embedding_dim, conf.hidden_dim
+
+    def syn(rows, cols, t, tid):
+        return OracleTensor.from_cpu(synth_weight(t, rows, cols, seed, tid, R.synth_scale(t, cols)), [rows, cols], t, odev)
+    rng = np.random.default_rng(seed)
+
+    def norm():
+        return OracleTensor.from_cpu((1.0 + 0.05 * rng.standard_normal(dim)).astype(np.float32), [dim], oc.F32, odev)
+    ra, rf = norm(), norm()
+    lw = LlamaWeights(None, [syn(dim, dim, wt, 1)], [syn(dim, dim, wt, 2)], [syn(dim, dim, wt, 3)], [syn(dim, dim, wt, 4)],
+                      [syn(hid, dim, wt, 5)], [syn(dim, hid, wt, 7)], [syn(hid, dim, wt, 6)], [ra], [rf], None, None)
+    lw.token_embed = syn(conf.vocab_size, dim, wt, 8)
+    lw.output_weight = syn(conf.vocab_size, dim, ct, 9)
+    lw.rms_final = norm()
+    oconf = OConf(32, 32, 1, dim, hid, 4096, 32000, 1e-5, 128)
+    ro = Llama2Runner(OracleTensor, oconf, lw, odev, 8)
+    want = [ro.forward([t], p).copy() for p, t in enumerate([1, 777, 31999])]
+    for exact in (True, False):
+        dev = make_device(exact_order=exact)
+        try:
+            w = R.synthetic_weights(dev, conf, wt, ct, seed=seed)
+            r = R.LlamaRunner(dev, conf, w, 8)
+            for p, t in enumerate([1, 777, 31999]):
+                got = r.forward([t], p).copy()
+                assert np.isfinite(got).all() and np.abs(got).max() > 1e-3
+                if exact:
+                    np.testing.assert_array_equal(got.view(np.uint32), want[p].view(np.uint32))
+                else:
+                    rel = np.abs(got - want[p]).max() / np.abs(want[p]).max()
+                    assert rel < 2e-2, rel          # one layer of order noise through truncating quantisers
+            r.close()
+        finally:
+            dev.close()
