@@ -72,11 +72,10 @@ def test_llama2_7b_shaped_layer_on_synthetic_weights(wt, ct):
     def norm():
         return OracleTensor.from_cpu((1.0 + 0.05 * rng.standard_normal(dim)).astype(np.float32), [dim], oc.F32, odev)
     ra, rf = norm(), norm()
-    lw = LlamaWeights(None, [syn(dim, dim, wt, 1)], [syn(dim, dim, wt, 2)], [syn(dim, dim, wt, 3)], [syn(dim, dim, wt, 4)],
-                      [syn(hid, dim, wt, 5)], [syn(dim, hid, wt, 7)], [syn(hid, dim, wt, 6)], [ra], [rf], None, None)
-    lw.token_embed = syn(conf.vocab_size, dim, wt, 8)
-    lw.output_weight = syn(conf.vocab_size, dim, ct, 9)
-    lw.rms_final = norm()
+    lw = LlamaWeights(token_embed=syn(conf.vocab_size, dim, wt, 8), wq=[syn(dim, dim, wt, 1)], wk=[syn(dim, dim, wt, 2)],
+                      wv=[syn(dim, dim, wt, 3)], wo=[syn(dim, dim, wt, 4)], ffn_gate_weight=[syn(hid, dim, wt, 5)],
+                      ffn_down_weight=[syn(dim, hid, wt, 7)], ffn_up_weight=[syn(hid, dim, wt, 6)], rms_att_weight=[ra],
+                      rms_ffn_weight=[rf], rms_final_weight=norm(), output_weight=syn(conf.vocab_size, dim, ct, 9))
     oconf = OConf(32, 32, 1, dim, hid, 4096, 32000, 1e-5, 128)
     ro = Llama2Runner(OracleTensor, oconf, lw, odev, 8)
     want = [ro.forward([t], p).copy() for p, t in enumerate([1, 777, 31999])]
