@@ -24,7 +24,8 @@
 // fully coalesced LDG.128; total bytes are unchanged (the f16 scales move to their own plane).
 //
 //   type   plane0                         plane1                 plane2            plane3
-//   Q8_0   qs  int8  [rows][k]            d   f16 [rows][k/32]
+//   Q8_0   qs  int8  [rows][k] (*)        d   f16 [rows][k/32]     (*) inside each group of 32 blocks the 16 B
+//                                                                  first halves precede the second halves
 //   Q4_0   qs  u8    [rows][k/32][16]     d   f16 [rows][k/32]
 //   Q4_1   qs  u8    [rows][k/32][16]     d,m f16x2
 //   Q5_0   qs  u8    [rows][k/32][16]     d   f16                qh u32 [rows][k/32]
@@ -174,6 +175,10 @@ int cc_launch_strided_copy(cc_device* dev, const void* src, int src_dtype, const
 int cc_launch_batch_matmul(cc_device* dev, const float* a, const void* b, int b_dtype, float* c,
                            int64_t a_batch, int64_t b_batch, int64_t m, int64_t k, int64_t n,
                            int64_t sb0, int64_t sb1, int64_t sb2);
+
+// ---- matvec_stream.cu --------------------------------------------------------------------------------
+bool cc_stream_supported(int type, int64_t k);
+int cc_launch_matvec_stream_plain(cc_device* dev, const cc_buf* w, const float* x, float* out, int64_t m, int64_t k);
 
 // ---- exact.cu (exact_order verification mode) -------------------------------------------------------
 int cc_launch_matvec_exact(cc_device* dev, int t, const uint8_t* w_gguf, const uint8_t* act_blocks, float* out,

@@ -62,25 +62,20 @@ struct TQ8_0 {
         stage(sm + al16i(k), d, k / 32 * 4);
     }
     static __device__ float row_dot(const WPlanes& W, int64_t row, int k, const uint8_t* sm, int lane) {
-        const int nchunk = k >> 4;                               // 16-byte chunks = half blocks
+        // device layout: groups of 32 blocks, first halves then second halves (matvec_stream.cu)
+        const int nb = k >> 5, nchunk = k >> 4;
         const int4* wq = (const int4*)W.p[0] + row * nchunk;
-        const uint16_t* wd = (const uint16_t*)W.p[1] + row * (k >> 5);
+        const uint16_t* wd = (const uint16_t*)W.p[1] + row * nb;
         const int4* aq = (const int4*)sm;
         const float* ad = (const float*)(sm + al16i(k));
         float acc = 0.0f;
-        int c = lane;
-        // main loop: 4 independent 16-byte loads in flight per lane
-        for (; c + 96 < nchunk; c += 128) {
-            int4 w0 = ld_stream_16(wq + c), w1 = ld_stream_16(wq + c + 32), w2 = ld_stream_16(wq + c + 64), w3 = ld_stream_16(wq + c + 96);
-            uint16_t h0 = wd[c >> 1], h1 = wd[(c + 32) >> 1], h2 = wd[(c + 64) >> 1], h3 = wd[(c + 96) >> 1];
-            acc += (float)dot16(w0, aq[c]) * h2f_bits(h0) * ad[c >> 1];
-            acc += (float)dot16(w1, aq[c + 32]) * h2f_bits(h1) * ad[(c + 32) >> 1];
-            acc += (float)dot16(w2, aq[c + 64]) * h2f_bits(h2) * ad[(c + 64) >> 1];
-            acc += (float)dot16(w3, aq[c + 96]) * h2f_bits(h3) * ad[(c + 96) >> 1];
-        }
-        for (; c < nchunk; c += 32) {
+        for (int c = lane; c < nchunk; c += 32) {
+            const int g = c >> 6, idx = c & 63;
+            const int nbg = min(32, nb - 32 * g);
+            const int half = idx >= nbg ? 1 : 0;
+            const int blk = 32 * g + idx - half * nbg;
             int4 w0 = ld_stream_16(wq + c);
-            acc += (float)dot16(w0, aq[c]) * h2f_bits(wd[c >> 1]) * ad[c >> 1];
+            acc += (float)dot16(w0, aq[2 * blk + half]) * h2f_bits(wd[blk]) * ad[blk];
         }
         return acc;
     }

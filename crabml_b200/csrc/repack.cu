@@ -54,7 +54,16 @@ struct RepackArgs {
     int src_off[CC_MAX_PLANES];
     int n;
     int block_bytes;
+    int q8_0_nb;          // > 0: plane 0 is the Q8_0 qs plane with `nb` blocks per row -> half-planar groups
 };
+
+// Q8_0 qs plane: byte j of block b (row-relative) -> offset inside the row.  Groups of 32 blocks; within a
+// group of nbg blocks all first halves (16 B) come first, then all second halves (matvec_stream.cu).
+__host__ __device__ inline int64_t q8_0_row_offset(int b, int j, int nb) {
+    int g = b >> 5, l = b & 31;
+    int nbg = nb - 32 * g < 32 ? nb - 32 * g : 32;
+    return (int64_t)g * 1024 + (j >> 4) * 16 * nbg + 16 * l + (j & 15);
+}
 
 // one thread per (block, plane byte): trivially parallel, load-time only
 template <bool TO_PLANES>
@@ -66,6 +75,11 @@ __global__ void repack_kernel(uint8_t* gguf, RepackArgs a, int64_t nblk, int pla
     int j = (int)(i - blk * pb);
     uint8_t* g = gguf + blk * a.block_bytes + a.src_off[plane] + j;
     uint8_t* p = a.plane[plane] + i;
+    if (a.q8_0_nb > 0 && plane == 0) {
+        int64_t row = blk / a.q8_0_nb;
+        int b = (int)(blk - row * a.q8_0_nb);
+        p = a.plane[0] + row * a.q8_0_nb * 32 + q8_0_row_offset(b, j, a.q8_0_nb);
+    }
     if (TO_PLANES) *p = *g; else *g = *p;
 }
 
@@ -74,6 +88,7 @@ static RepackArgs make_args(const cc_buf* b) {
     RepackArgs a;
     a.n = ps.n;
     a.block_bytes = (int)cc_block_bytes(b->dtype);
+    a.q8_0_nb = b->dtype == CC_Q8_0 ? (int)(b->cols / 32) : 0;
     for (int i = 0; i < CC_MAX_PLANES; i++) { a.plane[i] = b->plane[i]; a.bytes[i] = ps.bytes[i]; a.src_off[i] = ps.src_off[i]; }
     return a;
 }
@@ -108,7 +123,7 @@ int cc_launch_unrepack(cc_device* dev, const cc_buf* src, uint8_t* gguf_dev) {
 // Association of the float products follows the reference so results are BIT-EXACT
 // (file compiled with -fmad=false).
 // ---------------------------------------------------------------------------------------------------
-struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; };
+struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; int64_t cols; };
 
 __device__ __forceinline__ void get_scale_min_k4(int j, const uint8_t* q, uint8_t* d, uint8_t* m) {   // util.rs:18-27
     if (j < 4) {
@@ -126,7 +141,10 @@ __device__ float dequant_elem(int t, const DeqPlanes& P, int64_t e) {
     case CC_Q8_0: {                                                        // buf_q8_0.rs:18-23
         int64_t b = e >> 5;
         float d = h2f_bits(((const uint16_t*)P.p[1])[b]);
-        return (float)((const int8_t*)P.p[0])[e] * d;
+        const int nb = (int)(P.cols >> 5);
+        int64_t row = e / P.cols;
+        int64_t off = row * P.cols + q8_0_row_offset((int)(b - row * nb), (int)(e & 31), nb);
+        return (float)((const int8_t*)P.p[0])[off] * d;
     }
     case CC_Q4_0: {                                                        // buf_q4_0.rs:18-27
         int64_t b = e >> 5; int i = (int)(e & 31);
@@ -239,6 +257,7 @@ int cc_launch_dequant_rows(cc_device* dev, const cc_buf* src, const int64_t* row
                            void* dst, int dst_dtype) {
     DeqPlanes P;
     for (int i = 0; i < CC_MAX_PLANES; i++) P.p[i] = src->plane[i];
+    P.cols = src->cols > 0 ? src->cols : cols;
     int64_t total = (int64_t)n_rows * cols;
     if (total == 0) return CC_OK;
     dequant_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, dev->stream>>>(
