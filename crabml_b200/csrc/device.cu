@@ -294,9 +294,9 @@ extern "C" CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int3
     int rc = cc_launch_synth(dev, staging, t, n / be, seed, tensor_id, scale);
     if (rc == CC_OK) rc = cc_launch_repack(dev, staging, b);
     cudaError_t e2 = cudaStreamSynchronize(dev->stream);
-    cudaFree(staging);
+    if (dev->exact) b->raw = staging; else cudaFree(staging);
     if (rc == CC_OK && e2 != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "synth: %s", cudaGetErrorString(e2));
-    if (rc != CC_OK) { cudaFree(b->base); delete b; return rc; }
+    if (rc != CC_OK) { cudaFree(b->base); if (b->raw) cudaFree(b->raw); delete b; return rc; }
     *out = b;
     return CC_OK;
 }

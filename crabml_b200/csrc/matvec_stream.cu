@@ -126,22 +126,43 @@ __global__ void __launch_bounds__(MS_THREADS, MS_CTAS_PER_SM) matvec_stream_kern
     }
 
     // ---- 2. prologue under the latency of (1): [rms_norm * w] + Q8_0 quantisation of x into shared memory ----
-    float inv_scale_rms = 0.0f;
+    // All loads of a pass are issued before any is used (one L2 latency per pass, not one per block).
+    constexpr int PB = 8;                            // blocks per warp per pass
+    float rms = 0.0f;
     if (A.prologue == 1) {                           // rms_norm.rs:32-47 (sum order differs: tree)
         float ss = 0.0f;
-        for (int i = threadIdx.x; i < k; i += MS_THREADS) { float v = A.x[i]; ss += v * v; }
+        for (int i0 = 0; i0 < k; i0 += MS_THREADS * PB) {
+            float v[PB];
+#pragma unroll
+            for (int j = 0; j < PB; j++) { int i = i0 + j * MS_THREADS + threadIdx.x; v[j] = i < k ? A.x[i] : 0.0f; }
+#pragma unroll
+            for (int j = 0; j < PB; j++) ss += v[j] * v[j];
+        }
         ss = ms_block_sum(ss, s_red);
-        inv_scale_rms = sqrtf(ss / (float)k + A.eps);
+        rms = sqrtf(ss / (float)k + A.eps);
     }
-    for (int b = warp; b < nb; b += MS_WARPS) {      // one warp per 32-element block (buf_q8_0.rs:87-134)
-        float v = A.x[b * 32 + lane];
-        if (A.prologue == 1) v = (v / inv_scale_rms) * A.norm_w[b * 32 + lane];     // x/rms then * weight (llama2.rs:231-232)
-        float amax = warp_max(fabsf(v));
-        float d = amax / 127.0f;
-        int q = __float2int_rz(v / d);
-        s_q[b * 32 + lane] = (int8_t)q;
-        if constexpr (TYPE == CC_Q4_0) { int s = warp_sum_i(q); if (lane == 0) s_s[b] = s; }
-        if (lane == 0) s_d[b] = __half2float(__float2half_rn(d));
+    for (int b0 = 0; b0 < nb; b0 += MS_WARPS * PB) { // one warp per 32-element block (buf_q8_0.rs:87-134)
+        float v[PB], nw[PB];
+#pragma unroll
+        for (int j = 0; j < PB; j++) {
+            const int b = b0 + j * MS_WARPS + warp;
+            v[j] = b < nb ? A.x[b * 32 + lane] : 0.0f;
+            if (A.prologue == 1) nw[j] = b < nb ? A.norm_w[b * 32 + lane] : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < PB; j++) {
+            const int b = b0 + j * MS_WARPS + warp;
+            float x = v[j];
+            if (A.prologue == 1) x = (x / rms) * nw[j];          // x/rms then * weight (llama2.rs:231-232)
+            float amax = warp_max(fabsf(x));
+            float d = amax / 127.0f;
+            int q = __float2int_rz(x / d);
+            if (b < nb) {
+                s_q[b * 32 + lane] = (int8_t)q;
+                if constexpr (TYPE == CC_Q4_0) { int s = warp_sum_i(q); if (lane == 0) s_s[b] = s; }
+                if (lane == 0) s_d[b] = __half2float(__float2half_rn(d));
+            }
+        }
     }
     __syncthreads();
     const int4* aq = (const int4*)s_q;
