@@ -224,13 +224,6 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
     int rc = cc_new_activation(dev, b * m, CC_F32, false, &c);
     if (rc) return rc;
     const float* xf = (const float*)x->buf->plane[0];
-    if (!dev->exact && b == 1 && cc_stream_supported(wt, k)) {
-        // decode hot path: one launch, activation quantisation fused into the kernel prologue
-        rc = cc_launch_matvec_stream_plain(dev, w->buf, xf, (float*)c->base, m, k);
-        if (rc) { cc_tensor_release(c); return rc; }
-        *out = c;
-        return CC_OK;
-    }
     if (at != CC_F32) {
         rc = cc_ensure_act_scratch(dev, cc_act_bytes(at, b * k));
         if (!rc) rc = cc_launch_quantize(dev, xf, b * k, at, dev->act_scratch);     // matmul_vec.rs:37-40
@@ -247,6 +240,8 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
         const uint8_t* act = blocks ? (const uint8_t*)blocks : at == CC_F32 ? (const uint8_t*)xf : (const uint8_t*)dev->act_scratch;
         if (!rc) rc = cc_launch_matvec_exact(dev, wt, wraw, act, (float*)c->base, m, k, b);
         if (blocks) cc_pool_free(dev, blocks, cls);
+    } else if (!rc && b == 1 && cc_stream_supported(wt, k)) {
+        rc = cc_launch_matvec_stream_plain(dev, w->buf, dev->act_scratch, (float*)c->base, m, k);     // decode hot path
     } else if (!rc) rc = cc_launch_matvec(dev, w->buf, dev->act_scratch, xf, (float*)c->base, m, k, b);
     if (rc) { cc_tensor_release(c); return rc; }
     *out = c;

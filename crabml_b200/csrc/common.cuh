@@ -177,8 +177,24 @@ int cc_launch_batch_matmul(cc_device* dev, const float* a, const void* b, int b_
                            int64_t sb0, int64_t sb1, int64_t sb2);
 
 // ---- matvec_stream.cu --------------------------------------------------------------------------------
+struct StreamMats {           // up to 3 weight matrices sharing one activation (wq,wk,wv / gate,up)
+    const uint8_t* qs[3];
+    const uint16_t* d[3];
+    float* out[3];
+    int m[3];
+    int n;
+};
+struct StreamArgs {
+    StreamMats mats;
+    const void* act;         // ActQ8_0 scratch (quantize.cu layout) of k elements
+    int k;
+    int epilogue;            // 0 store, 1 add residual, 2 silu(mat0 row) * (mat1 row)
+    const float* residual;
+    const uint16_t* exp_lut;
+};
 bool cc_stream_supported(int type, int64_t k);
-int cc_launch_matvec_stream_plain(cc_device* dev, const cc_buf* w, const float* x, float* out, int64_t m, int64_t k);
+int cc_launch_matvec_stream(cc_device* dev, int type, const StreamArgs& A);
+int cc_launch_matvec_stream_plain(cc_device* dev, const cc_buf* w, const void* act, float* out, int64_t m, int64_t k);
 
 // ---- exact.cu (exact_order verification mode) -------------------------------------------------------
 int cc_launch_matvec_exact(cc_device* dev, int t, const uint8_t* w_gguf, const uint8_t* act_blocks, float* out,
