@@ -81,6 +81,8 @@ def load_library(build_if_missing: bool = True):
         "cc_last_error": (C.c_char_p, [vp]),
         "cc_device_synchronize": (i32, [vp]),
         "cc_device_launch_count": (u64, [vp]),
+        "cc_device_flush": (i32, [vp]),
+        "cc_lazy_stats": (i32, [vp, C.POINTER(u64)]),
         "cc_device_stream": (vp, [vp]),
         "cc_tensor_from_cpu": (i32, [vp, vp, sz, C.POINTER(i64), i32, i32, pp]),
         "cc_tensor_alloc": (i32, [vp, C.POINTER(i64), i32, i32, pp]),

@@ -26,6 +26,16 @@ static bool view_ok(const cc_view* v) { return v && v->buf && v->ndim >= 1 && v-
         if (!(dev)) return CC_ERR_ARG;                                                   \
         if (!view_ok(v)) return cc_fail((dev), CC_ERR_ARG, "%s: bad tensor view", what); \
     } while (0)
+// lazy mode (lazy.cu): after the same argument checks as eager mode the op is queued instead of launched
+enum { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU };
+int cc_lazy_record(cc_device* dev, int kind, const cc_view* a, const cc_view* b, cc_buf* out, float f, int64_t i0, int64_t i1, int64_t i2,
+                   const int64_t* rows, int n_rows);
+#define LAZY(dev) ((dev)->lz != nullptr && !(dev)->exact)
+#define FLUSH(dev)                                  \
+    do {                                            \
+        if (LAZY(dev)) { int _rc = cc_lazy_flush(dev); if (_rc) return _rc; } \
+    } while (0)
+
 #define REQUIRE_F32(dev, v, what) CC_REQUIRE(dev, (v)->buf->dtype == CC_F32, "%s: not f32, but got type %d", what, (v)->buf->dtype)
 
 // ---- dup / export / contiguous ----------------------------------------------------------------------------------
@@ -39,8 +49,9 @@ extern "C" CC_API int cc_tensor_dup(cc_device* dev, const cc_view* src, cc_buf**
     cc_buf* b = nullptr;
     int rc = cc_new_activation(dev, n, CC_F32, false, &b);
     if (rc) return rc;
-    if (n) CC_CUDA(dev, cudaMemcpyAsync(b->base, src->buf->plane[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, dev->stream));
     *out = b;
+    if (LAZY(dev)) return cc_lazy_record(dev, L_DUP, src, nullptr, b, 0, 0, 0, 0, nullptr, 0);
+    if (n) CC_CUDA(dev, cudaMemcpyAsync(b->base, src->buf->plane[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, dev->stream));
     return CC_OK;
 }
 
@@ -49,6 +60,7 @@ extern "C" CC_API int cc_tensor_export_f32(cc_device* dev, const cc_view* src, f
     if (!dst) return cc_fail(dev, CC_ERR_ARG, "export: dst is NULL");
     REQUIRE_F32(dev, src, "export");
     CC_REQUIRE(dev, view_contiguous(src), "export: tensor is not contiguous");
+    FLUSH(dev);
     int64_t len = view_len(src);
     size_t cnt = n < (size_t)len ? n : (size_t)len;
     if (cnt) CC_CUDA(dev, cudaMemcpyAsync(dst, src->buf->plane[0], cnt * 4, cudaMemcpyDeviceToHost, dev->stream));
@@ -74,6 +86,7 @@ extern "C" CC_API int cc_contiguous(cc_device* dev, const cc_view* src, cc_buf**
     int64_t dstr[CC_MAX_DIMS];
     int64_t s = 1;
     for (int i = src->ndim - 1; i >= 0; i--) { dstr[i] = s; s *= src->shape[i]; }
+    if (LAZY(dev)) { *out = b; return cc_lazy_record(dev, L_CONTIGUOUS, src, nullptr, b, 0, 0, 0, 0, nullptr, 0); }
     rc = cc_launch_strided_copy(dev, src->buf->plane[0], t, src->shape, src->strides, b->base, t, dstr, 0, src->ndim);
     if (rc) { cc_tensor_release(b); return rc; }
     *out = b;
@@ -99,6 +112,7 @@ extern "C" CC_API int cc_concatenate(cc_device* dev, const cc_view* self, const 
         if (top >= 0) hi += top * self->strides[i];
     }
     CC_REQUIRE(dev, view_len(rhs) == 0 || hi < self->buf->nelems, "concatenate: exceeds the pre-allocated storage");
+    if (LAZY(dev)) return cc_lazy_record(dev, L_CONCAT, self, rhs, nullptr, 0, axis, 0, 0, nullptr, 0);
     return cc_launch_strided_copy(dev, rhs->buf->plane[0], t2, rhs->shape, rhs->strides, self->buf->plane[0], t1,
                                   self->strides, self->shape[axis] * self->strides[axis], self->ndim);
 }
@@ -121,6 +135,7 @@ extern "C" CC_API int cc_copy_rows_from(cc_device* dev, const cc_view* dst, cons
     for (int i = 0; i < n_rows; i++)
         CC_REQUIRE(dev, rows[i] >= 0 && (rows[i] + 1) * cols <= src_len, "copy_rows_from: row %lld out of range", (long long)rows[i]);
     if (n_rows == 0) return CC_OK;
+    if (LAZY(dev)) return cc_lazy_record(dev, L_COPY_ROWS, dst, src, nullptr, 0, 0, 0, 0, rows, n_rows);
     int rc = cc_ensure_dev_idx(dev, (size_t)n_rows * 8);
     if (rc) return rc;
     rc = cc_ensure_pinned(dev, (size_t)n_rows * 8);
@@ -141,6 +156,7 @@ extern "C" CC_API int cc_rope_inplace(cc_device* dev, const cc_view* x, int32_t 
     if (x->ndim == 2) { n_batch = 1; stride = view_len(x); hd = x->shape[1]; }
     else { n_batch = x->shape[0]; stride = x->strides[0]; hd = x->shape[2]; }
     CC_REQUIRE(dev, rope_dims >= 0 && rope_dims <= hd && rope_dims % 2 == 0, "rope_inplace: bad rope_dims %lld", (long long)rope_dims);
+    if (LAZY(dev)) return cc_lazy_record(dev, L_ROPE, x, nullptr, nullptr, (float)mode, pos, n_batch, stride, &rope_dims, 1);
     // cos/sin are evaluated on the host with the same libm calls as the reference (rope.rs:52-53,74-75) in both
     // modes: bit-exact, and no slow large-argument device sinf/cosf
     return cc_launch_rope_exact(dev, (float*)x->buf->plane[0], n_batch, stride, hd, mode, pos, rope_dims);
@@ -153,6 +169,7 @@ extern "C" CC_API int cc_rms_norm_inplace(cc_device* dev, const cc_view* x, floa
     REQUIRE_F32(dev, x, "rms_norm_inplace");
     int64_t rows = x->ndim == 1 ? 1 : x->shape[0], cols = x->ndim == 1 ? x->shape[0] : x->shape[1];
     CC_REQUIRE(dev, cols % 32 == 0, "rms_norm_inplace: length %lld %% 32 != 0", (long long)cols);   // rms_norm.rs:34
+    if (LAZY(dev)) return cc_lazy_record(dev, L_RMS_NORM, x, nullptr, nullptr, eps, 0, 0, 0, nullptr, 0);
     if (dev->exact) return cc_launch_rms_norm_exact(dev, (float*)x->buf->plane[0], rows, cols, eps);
     return cc_launch_rms_norm(dev, (float*)x->buf->plane[0], rows, cols, eps);
 }
@@ -164,6 +181,7 @@ extern "C" CC_API int cc_softmax_inplace(cc_device* dev, const cc_view* x, int32
     REQUIRE_F32(dev, x, "softmax_inplace");
     CC_REQUIRE(dev, axis == x->ndim - 1, "only axis=%d is supported on a %d dimensions tensor", x->ndim - 1, x->ndim);
     int64_t cols = x->shape[x->ndim - 1];
+    if (LAZY(dev)) return cc_lazy_record(dev, L_SOFTMAX, x, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0);
     if (dev->exact) return cc_launch_softmax_exact(dev, (float*)x->buf->plane[0], cols ? view_len(x) / cols : 0, cols);
     return cc_launch_softmax(dev, (float*)x->buf->plane[0], cols ? view_len(x) / cols : 0, cols);
 }
@@ -171,11 +189,13 @@ extern "C" CC_API int cc_softmax_inplace(cc_device* dev, const cc_view* x, int32
 extern "C" CC_API int cc_silu_inplace(cc_device* dev, const cc_view* x) {                   // silu.rs:6-13: whole buffer
     CHECK_VIEW(dev, x, "silu_inplace");
     REQUIRE_F32(dev, x, "silu_inplace");
+    if (LAZY(dev)) return cc_lazy_record(dev, L_SILU, x, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0);
     return cc_launch_silu(dev, (float*)x->buf->plane[0], view_len(x));
 }
 extern "C" CC_API int cc_gelu_inplace(cc_device* dev, const cc_view* x) {                   // gelu.rs:10-15
     CHECK_VIEW(dev, x, "gelu_inplace");
     REQUIRE_F32(dev, x, "gelu_inplace");
+    if (LAZY(dev)) return cc_lazy_record(dev, L_GELU, x, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0);
     return cc_launch_gelu(dev, (float*)x->buf->plane[0], view_len(x));
 }
 
@@ -193,6 +213,7 @@ static int binary(cc_device* dev, const cc_view* x, const cc_view* rhs, int op, 
         ny -= ny % 4;
         if (ny == 0) return CC_OK;
     }
+    if (LAZY(dev)) return cc_lazy_record(dev, op == 1 ? L_MUL : L_ADD, x, rhs, nullptr, 0, n, ny, 0, nullptr, 0);
     return cc_launch_binary(dev, (float*)x->buf->plane[0], n, (const float*)rhs->buf->plane[0], ny, op);
 }
 extern "C" CC_API int cc_mul_inplace(cc_device* dev, const cc_view* x, const cc_view* rhs) { return binary(dev, x, rhs, 1, "mul_inplace"); }
@@ -201,6 +222,7 @@ extern "C" CC_API int cc_scale_inplace(cc_device* dev, const cc_view* x, float r
     CHECK_VIEW(dev, x, "scale_inplace");
     REQUIRE_F32(dev, x, "scale_inplace");
     CC_REQUIRE(dev, view_contiguous(x), "scale_inplace: not contiguous");
+    if (LAZY(dev)) return cc_lazy_record(dev, L_SCALE, x, nullptr, nullptr, rhs, 0, 0, 0, nullptr, 0);
     return cc_launch_scale(dev, (float*)x->buf->plane[0], view_len(x), rhs);
 }
 
@@ -223,6 +245,7 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
     cc_buf* c = nullptr;
     int rc = cc_new_activation(dev, b * m, CC_F32, false, &c);
     if (rc) return rc;
+    if (LAZY(dev)) { *out = c; return cc_lazy_record(dev, L_MATVEC, w, x, c, 0, 0, 0, 0, nullptr, 0); }
     const float* xf = (const float*)x->buf->plane[0];
     if (at != CC_F32) {
         rc = cc_ensure_act_scratch(dev, cc_act_bytes(at, b * k));
@@ -266,6 +289,7 @@ extern "C" CC_API int cc_batch_matmul(cc_device* dev, const cc_view* a, const cc
     cc_buf* c = nullptr;
     int rc = cc_new_activation(dev, ab * m * n, CC_F32, false, &c);
     if (rc) return rc;
+    if (LAZY(dev)) { *out = c; return cc_lazy_record(dev, L_BMM, a, b, c, 0, 0, 0, 0, nullptr, 0); }
     if (dev->exact && b->strides[1] == 1)
         rc = cc_launch_bmm_kcontig_exact(dev, (const float*)a->buf->plane[0], b->buf->plane[0], bt, (float*)c->base, ab, bb, m, k, n,
                                          b->strides[0], b->strides[2]);
@@ -283,6 +307,7 @@ extern "C" CC_API int cc_debug_tensor_tap(cc_device* dev, const char* name, cons
     if (!name) return cc_fail(dev, CC_ERR_ARG, "with_name: name is NULL");
     if (!dev->debug_named_tensors) return CC_OK;
     REQUIRE_F32(dev, x, "with_name");
+    FLUSH(dev);
     int64_t n = view_len(x);                     // the reference snapshots the whole buffer; callers tap dense tensors
     std::vector<float> host((size_t)n);
     if (n) CC_CUDA(dev, cudaMemcpyAsync(host.data(), x->buf->plane[0], (size_t)n * 4, cudaMemcpyDeviceToHost, dev->stream));
@@ -311,6 +336,7 @@ extern "C" CC_API int cc_test_quantize_activation(cc_device* dev, const cc_view*
     CC_REQUIRE(dev, n % be == 0, "quantize_activation: length %lld %% %d != 0", (long long)n, be);
     size_t need = (size_t)(n / be) * cc_block_bytes(act_type);
     CC_REQUIRE(dev, nbytes >= need, "quantize_activation: %zu bytes given, %zu needed", nbytes, need);
+    FLUSH(dev);
     int rc = cc_ensure_act_scratch(dev, cc_act_bytes(act_type, n));
     if (rc) return rc;
     rc = cc_launch_quantize(dev, (const float*)x->buf->plane[0], n, act_type, dev->act_scratch);

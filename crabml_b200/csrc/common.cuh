@@ -76,6 +76,8 @@ struct cc_device {
     bool debug_named_tensors = false;
     bool lazy = false;
     bool exact = false;       // cc_device_options.exact_order
+    bool pdl = true;          // launch fused-path kernels with programmatic dependent launch
+    struct LazyState* lz = nullptr;   // non-null in lazy mode (lazy.cu)
     std::string last_error;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -192,6 +194,23 @@ struct StreamArgs {
     const float* residual;
     const uint16_t* exp_lut;
 };
+struct AttnArgs {            // fused decode attention (fused.cu)
+    const float *q, *k, *v;  // raw matvec outputs [n_heads*hd], [n_kv*hd], [n_kv*hd]
+    void *kcache, *vcache;   // [n_kv, seq_max, hd] F32 or F16
+    float* out;              // [n_heads*hd]
+    void* act_scratch;       // Q8_0 quantisation of out
+    const int64_t* dyn;      // device: {pos, kv_len}
+    const float* rope_tab;   // device: cos[rope_dim/2], sin[rope_dim/2]
+    int n_heads, n_kv, hd, rope_dim, max_len, kv_f16;
+    int64_t seq_stride;
+    float scale;
+};
+int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch);
+int cc_launch_attn_decode(cc_device* dev, const AttnArgs& a);
+struct LazyState;
+LazyState* cc_lazy_create(cc_device* dev);
+void cc_lazy_destroy(cc_device* dev);
+int cc_lazy_flush(cc_device* dev);
 bool cc_stream_supported(int type, int64_t k);
 int cc_launch_matvec_stream(cc_device* dev, int type, const StreamArgs& A);
 int cc_launch_matvec_stream_plain(cc_device* dev, const cc_buf* w, const void* act, float* out, int64_t m, int64_t k);

@@ -87,6 +87,10 @@ extern "C" CC_API int cc_device_create(const cc_device_options* opts, cc_device*
     CREATE_CUDA(cudaMalloc(&dev->gelu_lut, 65536 * 2));
     CREATE_CUDA(cudaMemcpy(dev->gelu_lut, lut.data(), 65536 * 2, cudaMemcpyHostToDevice));
 #undef CREATE_CUDA
+    if (dev->lazy && !dev->exact) {
+        dev->lz = cc_lazy_create(dev);
+        if (!dev->lz) { cc_fail(nullptr, CC_ERR_CUDA, "lazy mode: could not allocate the dynamic-argument buffers"); delete dev; return CC_ERR_CUDA; }
+    }
     *out = dev;
     return CC_OK;
 }
@@ -95,6 +99,7 @@ extern "C" CC_API void cc_device_destroy(cc_device* dev) {
     if (!dev) return;
     cudaSetDevice(dev->ordinal);
     cudaStreamSynchronize(dev->stream);
+    cc_lazy_destroy(dev);
     for (auto& kv : dev->free_lists)
         for (void* p : kv.second) cudaFree(p);
     if (dev->act_scratch) cudaFree(dev->act_scratch);
@@ -112,18 +117,25 @@ extern "C" CC_API void* cc_device_stream(cc_device* dev) { return dev ? (void*)d
 
 extern "C" CC_API int cc_device_synchronize(cc_device* dev) {
     if (!dev) return CC_ERR_ARG;
+    if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
     return CC_OK;
+}
+extern "C" CC_API int cc_device_flush(cc_device* dev) {
+    if (!dev) return CC_ERR_ARG;
+    return dev->lz ? cc_lazy_flush(dev) : CC_OK;
 }
 
 extern "C" CC_API int cc_bench_timer_begin(cc_device* dev) {
     if (!dev) return CC_ERR_ARG;
     if (!dev->ev_begin) { CC_CUDA(dev, cudaEventCreate(&dev->ev_begin)); CC_CUDA(dev, cudaEventCreate(&dev->ev_end)); }
+    if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_CUDA(dev, cudaEventRecord(dev->ev_begin, dev->stream));
     return CC_OK;
 }
 extern "C" CC_API int cc_bench_timer_end(cc_device* dev, float* ms) {
     if (!dev || !ms || !dev->ev_begin) return CC_ERR_ARG;
+    if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_CUDA(dev, cudaEventRecord(dev->ev_end, dev->stream));
     CC_CUDA(dev, cudaEventSynchronize(dev->ev_end));
     CC_CUDA(dev, cudaEventElapsedTime(ms, dev->ev_begin, dev->ev_end));
@@ -303,6 +315,7 @@ extern "C" CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int3
 
 extern "C" CC_API int cc_test_export_blocks(cc_device* dev, const cc_buf* buf, void* dst, size_t nbytes) {
     if (!dev || !buf || !dst) return cc_fail(dev, CC_ERR_ARG, "cc_test_export_blocks: bad argument");
+    if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_REQUIRE(dev, cc_is_quant(buf->dtype), "export_blocks: not a quantized tensor");
     size_t need = (size_t)(buf->nelems / cc_block_elems(buf->dtype)) * cc_block_bytes(buf->dtype);
     CC_REQUIRE(dev, nbytes >= need, "export_blocks: %zu bytes given, %zu needed", nbytes, need);

@@ -38,6 +38,7 @@ void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float*
     const CudaTensor& ow = output_weight.valid() ? output_weight : token_embed;
     CudaTensor lg = ow.matmul_vec(x_final);
     if (logits_out) lg.export_to(logits_out, (size_t)conf.vocab_size);
+    else CudaTensor::check(dev, cc_device_flush(dev));     // lazy mode: submit this token's work without a host sync
 }
 
 // llama2.rs:213-281

@@ -1,0 +1,484 @@
+// lazy.cu -- lazy mode: record the trait calls of one forward(), fuse, replay as a CUDA graph.
+//
+// The reference's Tensor API is eager: ~31 calls per layer, ~1000 per token, each a separate launch in
+// eager mode.  profiles/r01c shows that per-launch overhead, not kernel bodies, is what caps decode.  In lazy mode the
+// SAME C-ABI calls only append to a queue (after the same argument checks); the queue is executed at the first call that
+// needs a result on the host (export / debug tap / synchronize -- the reference synchronises only there too, llama2.rs:209):
+//   1. fuse: runs of ops that match the Llama decode layer (llama2.rs:226-269, 527-638) are replaced by the kernels of
+//      fused.cu / matvec_stream.cu; anything unrecognised falls back to its eager kernel, in order;
+//   2. the resulting launch list is hashed (kernel ids, pointers, static sizes).  Values that change every token
+//      (position, KV length, token ids, RoPE table) live in a small device buffer `dyn` that the kernels read;
+//   3. first time a hash is seen the launches are stream-captured into a CUDA graph (programmatic-dependent-launch edges
+//      included); afterwards a token = one 1-2 KB H2D copy of `dyn` + one cudaGraphLaunch.
+// The activation pool hands out the same pointers for the same call sequence (LIFO free lists), which is what makes the
+// hash stable from token to token.
+#include <math.h>
+#include <string.h>
+
+#include <functional>
+
+#include "common.cuh"
+
+enum LKind { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU };
+
+struct LView { cc_buf* buf = nullptr; int ndim = 0; int64_t shape[CC_MAX_DIMS] = {0, 0, 0, 0}, strides[CC_MAX_DIMS] = {0, 0, 0, 0}; };
+
+struct LOp {
+    int kind;
+    LView a, b;              // a: self / lhs / dst ; b: rhs / src
+    cc_buf* out = nullptr;   // freshly allocated result (MATVEC, BMM, DUP, CONTIGUOUS)
+    float f = 0.0f;
+    int64_t i0 = 0, i1 = 0, i2 = 0;
+    std::vector<int64_t> rows;
+    bool done = false;
+};
+
+struct GraphEntry { cudaGraphExec_t exec = nullptr; size_t dyn_bytes = 0; uint64_t launches = 0; };
+
+struct LazyState {
+    std::vector<LOp> q;
+    std::unordered_map<cc_buf*, int> qrefs;
+    uint8_t* dyn_host[2] = {nullptr, nullptr};     // pinned, alternated so the host can build token t+1 while t runs
+    cudaEvent_t dyn_ev[2] = {nullptr, nullptr};
+    int dyn_slot = 0;
+    uint8_t* dyn_dev = nullptr;
+    size_t dyn_cap = 1 << 16;
+    void* act[2] = {nullptr, nullptr};
+    size_t act_cap = 0;
+    std::unordered_map<uint64_t, GraphEntry> cache;
+    uint64_t flushes = 0, graph_hits = 0, captures = 0, uncached = 0;
+};
+
+static LView mkview(const cc_view* v) {
+    LView l;
+    if (!v) return l;
+    l.buf = v->buf; l.ndim = v->ndim;
+    for (int i = 0; i < v->ndim; i++) { l.shape[i] = v->shape[i]; l.strides[i] = v->strides[i]; }
+    return l;
+}
+static int64_t vlen(const LView& v) { int64_t n = 1; for (int i = 0; i < v.ndim; i++) n *= v.shape[i]; return n; }
+static bool vcontig(const LView& v) {
+    if (v.ndim == 0) return true;
+    if (v.strides[v.ndim - 1] != 1) return false;
+    int64_t last = 1;
+    for (int i = v.ndim - 1; i >= 0; i--) { if (last != v.strides[i]) return false; last *= v.shape[i]; }
+    return true;
+}
+
+LazyState* cc_lazy_create(cc_device* dev) {
+    LazyState* lz = new LazyState();
+    for (int i = 0; i < 2; i++)
+        if (cudaMallocHost(&lz->dyn_host[i], lz->dyn_cap) != cudaSuccess || cudaEventCreateWithFlags(&lz->dyn_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete lz; return nullptr; }
+    if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
+    return lz;
+}
+void cc_lazy_destroy(cc_device* dev) {
+    LazyState* lz = dev->lz;
+    if (!lz) return;
+    for (auto& op : lz->q) { if (op.a.buf) cc_tensor_release(op.a.buf); if (op.b.buf) cc_tensor_release(op.b.buf); if (op.out) cc_tensor_release(op.out); }
+    for (auto& kv : lz->cache) cudaGraphExecDestroy(kv.second.exec);
+    for (int i = 0; i < 2; i++) { if (lz->dyn_host[i]) cudaFreeHost(lz->dyn_host[i]); if (lz->dyn_ev[i]) cudaEventDestroy(lz->dyn_ev[i]); }
+    if (lz->dyn_dev) cudaFree(lz->dyn_dev);
+    for (int i = 0; i < 2; i++) if (lz->act[i]) cudaFree(lz->act[i]);
+    delete lz;
+    dev->lz = nullptr;
+}
+
+// ---- recording ---------------------------------------------------------------------------------------------------
+static void hold(LazyState* lz, cc_buf* b) { if (b) { cc_tensor_retain(b); lz->qrefs[b]++; } }
+
+int cc_lazy_record(cc_device* dev, int kind, const cc_view* a, const cc_view* b, cc_buf* out, float f, int64_t i0, int64_t i1, int64_t i2,
+                   const int64_t* rows, int n_rows) {
+    LazyState* lz = dev->lz;
+    LOp op;
+    op.kind = kind; op.a = mkview(a); op.b = mkview(b); op.out = out; op.f = f; op.i0 = i0; op.i1 = i1; op.i2 = i2;
+    if (rows) op.rows.assign(rows, rows + n_rows);
+    hold(lz, op.a.buf); hold(lz, op.b.buf); hold(lz, op.out);
+    lz->q.push_back(std::move(op));
+    return CC_OK;
+}
+
+// ---- plan building ---------------------------------------------------------------------------------------------------
+struct Plan {
+    std::vector<uint64_t> sig;
+    std::vector<uint8_t> dyn;
+    std::vector<std::function<int(uint8_t* dyn_dev)>> steps;
+    bool cacheable = true;
+    void S(uint64_t v) { sig.push_back(v); }
+    void SP(const void* p) { sig.push_back((uint64_t)(uintptr_t)p); }
+    size_t dyn_put(const void* p, size_t n) {
+        size_t off = (dyn.size() + 15) & ~(size_t)15;
+        dyn.resize(off + n);
+        memcpy(dyn.data() + off, p, n);
+        return off;
+    }
+};
+
+static uint64_t hash_sig(const std::vector<uint64_t>& s) {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t v : s) { h ^= v; h *= 1099511628211ull; h ^= h >> 29; }
+    return h;
+}
+
+struct Fuser {
+    cc_device* dev;
+    LazyState* lz;
+    std::vector<LOp>& q;
+    Plan& P;
+    size_t rope_off = (size_t)-1; int64_t rope_pos = -1; int rope_hd = 0, rope_dim = 0;
+
+    bool is(size_t i, int kind) const { return i < q.size() && !q[i].done && q[i].kind == kind; }
+    // no op after `from` touches buf, and nobody outside the queue holds it
+    bool dead_after(cc_buf* b, size_t from) const {
+        for (size_t j = from; j < q.size(); j++)
+            if (q[j].a.buf == b || q[j].b.buf == b || q[j].out == b) return false;
+        auto it = lz->qrefs.find(b);
+        int held = it == lz->qrefs.end() ? 0 : it->second;
+        return b->refs.load() == held;
+    }
+    static bool same_dense_1xN(const LView& v, int64_t n) { return vcontig(v) && vlen(v) == n; }
+
+    // ---- eager fallback for one op -----------------------------------------------------------------------------
+    void fallback(size_t i) {
+        LOp op = q[i];       // copy: lambdas outlive the queue only until flush ends, but keep them self-contained
+        cc_device* d = dev;
+        P.S(0x1000 + op.kind); P.SP(op.a.buf ? op.a.buf->plane[0] : nullptr); P.SP(op.b.buf ? op.b.buf->plane[0] : nullptr);
+        P.SP(op.out ? op.out->plane[0] : nullptr);
+        for (int k = 0; k < CC_MAX_DIMS; k++) { P.S(op.a.shape[k]); P.S(op.a.strides[k]); P.S(op.b.shape[k]); P.S(op.b.strides[k]); }
+        P.S(op.i0); P.S(op.i1); P.S(op.i2); uint32_t fb; memcpy(&fb, &op.f, 4); P.S(fb);
+        switch (op.kind) {
+        case L_ROPE: case L_CONCAT: case L_BMM: case L_SOFTMAX: P.cacheable = false; break;   // position / length dependent
+        case L_COPY_ROWS: P.cacheable = false; break;   // (normally taken by try_copy_rows) host row list would be baked into a graph
+        default: break;
+        }
+        for (int64_t r : op.rows) P.S((uint64_t)r);
+        P.steps.push_back([d, op](uint8_t*) -> int {
+            const LView &a = op.a, &b = op.b;
+            switch (op.kind) {
+            case L_DUP: {
+                int64_t n = vlen(a);
+                if (n && cudaMemcpyAsync(op.out->base, a.buf->plane[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, d->stream) != cudaSuccess) return cc_fail(d, CC_ERR_CUDA, "dup copy failed");
+                return CC_OK;
+            }
+            case L_RMS_NORM: return cc_launch_rms_norm(d, (float*)a.buf->plane[0], a.ndim == 1 ? 1 : a.shape[0], a.shape[a.ndim - 1], op.f);
+            case L_MUL: return cc_launch_binary(d, (float*)a.buf->plane[0], op.i0, (const float*)b.buf->plane[0], op.i1, 1);
+            case L_ADD: return cc_launch_binary(d, (float*)a.buf->plane[0], op.i0, (const float*)b.buf->plane[0], op.i1, 0);
+            case L_SCALE: return cc_launch_scale(d, (float*)a.buf->plane[0], vlen(a), op.f);
+            case L_SILU: return cc_launch_silu(d, (float*)a.buf->plane[0], vlen(a));
+            case L_GELU: return cc_launch_gelu(d, (float*)a.buf->plane[0], vlen(a));
+            case L_SOFTMAX: { int64_t cols = a.shape[a.ndim - 1]; return cc_launch_softmax(d, (float*)a.buf->plane[0], cols ? vlen(a) / cols : 0, cols); }
+            case L_ROPE: return cc_launch_rope_exact(d, (float*)a.buf->plane[0], op.i1, op.i2, a.shape[a.ndim - 1], (int)op.f, op.i0, op.rows[0]);
+            case L_CONCAT:
+                return cc_launch_strided_copy(d, b.buf->plane[0], b.buf->dtype, b.shape, b.strides, a.buf->plane[0], a.buf->dtype, a.strides,
+                                              a.shape[op.i0] * a.strides[op.i0], a.ndim);
+            case L_CONTIGUOUS: {
+                int64_t dstr[CC_MAX_DIMS]; int64_t s = 1;
+                for (int k = a.ndim - 1; k >= 0; k--) { dstr[k] = s; s *= a.shape[k]; }
+                return cc_launch_strided_copy(d, a.buf->plane[0], a.buf->dtype, a.shape, a.strides, op.out->base, a.buf->dtype, dstr, 0, a.ndim);
+            }
+            case L_BMM:
+                return cc_launch_batch_matmul(d, (const float*)a.buf->plane[0], b.buf->plane[0], b.buf->dtype, (float*)op.out->base, a.shape[0], b.shape[0],
+                                              a.shape[1], a.shape[2], b.shape[2], b.strides[0], b.strides[1], b.strides[2]);
+            case L_COPY_ROWS: {
+                int n = (int)op.rows.size();
+                int rc = cc_ensure_dev_idx(d, (size_t)n * 8);
+                if (rc) return rc;
+                if (cudaMemcpyAsync(d->dev_idx, op.rows.data(), (size_t)n * 8, cudaMemcpyHostToDevice, d->stream) != cudaSuccess) return cc_fail(d, CC_ERR_CUDA, "row index upload failed");
+                return cc_launch_dequant_rows(d, b.buf, (const int64_t*)d->dev_idx, n, a.shape[a.ndim - 1], a.buf->plane[0], a.buf->dtype);
+            }
+            case L_MATVEC: {
+                const int64_t m = a.shape[0], k = a.shape[1], bb = b.ndim == 1 ? 1 : b.shape[0];
+                const int wt = a.buf->dtype, at = cc_partner_type(wt);
+                const float* xf = (const float*)b.buf->plane[0];
+                int rc = CC_OK;
+                if (at != CC_F32) rc = cc_launch_quantize(d, xf, bb * k, at, d->act_scratch);
+                if (rc) return rc;
+                if (bb == 1 && cc_stream_supported(wt, k)) return cc_launch_matvec_stream_plain(d, a.buf, d->act_scratch, (float*)op.out->base, m, k);
+                return cc_launch_matvec(d, a.buf, d->act_scratch, xf, (float*)op.out->base, m, k, bb);
+            }
+            }
+            return cc_fail(d, CC_ERR_UNSUPPORTED, "lazy: unknown op kind %d", op.kind);
+        });
+        q[i].done = true;
+    }
+
+    // ---- pattern: [DUP] RMS_NORM MUL -> normq ; returns number of ops consumed (0 = no match) ---------------------------------
+    // On success *act_sel receives the scratch index that now holds quantize(x).
+    size_t try_normq(size_t i, int act_sel, cc_buf** xbuf) {
+        size_t j = i;
+        cc_buf* orig = nullptr;
+        if (is(j, L_DUP) && is(j + 1, L_RMS_NORM) && q[j + 1].a.buf == q[j].a.buf) { orig = q[j].out; j++; }
+        if (!(is(j, L_RMS_NORM) && is(j + 1, L_MUL))) return 0;
+        const LOp &rn = q[j], &mu = q[j + 1];
+        if (mu.a.buf != rn.a.buf) return 0;
+        const int64_t n = vlen(rn.a);
+        if (rn.a.ndim > 2 || (rn.a.ndim == 2 && rn.a.shape[0] != 1) || !vcontig(rn.a) || n % 32) return 0;
+        if (vlen(mu.b) != n || mu.b.buf->dtype != CC_F32 || !vcontig(mu.b)) return 0;
+        if (n > 65536) return 0;
+        float* x = (float*)rn.a.buf->plane[0];
+        float* og = orig ? (float*)orig->base : nullptr;
+        const float* w = (const float*)mu.b.buf->plane[0];
+        float eps = rn.f;
+        void* act = lz->act[act_sel];
+        cc_device* d = dev;
+        P.S(0x2001); P.SP(x); P.SP(og); P.SP(w); P.SP(act); P.S((uint64_t)n); uint32_t eb; memcpy(&eb, &eps, 4); P.S(eb);
+        P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, og, w, eps, n, act); });
+        *xbuf = rn.a.buf;
+        size_t used = (j + 2) - i;
+        for (size_t t = i; t < i + used; t++) q[t].done = true;
+        return used;
+    }
+
+    // ---- pattern: 1-3 MATVECs on the same activation through the streaming kernel (+ optional epilogues) ------------------------------
+    // `act_sel` >= 0: scratch already holds quantize(x) ; < 0: emit a plain quantise first.
+    size_t try_stream(size_t i, cc_buf* xbuf, int act_sel) {
+        if (!is(i, L_MATVEC)) return 0;
+        const LOp& m0 = q[i];
+        const int wt = m0.a.buf->dtype;
+        const int64_t k = m0.a.shape[1];
+        if (!cc_stream_supported(wt, k) || m0.b.buf != xbuf || vlen(m0.b) != k || !vcontig(m0.b)) return 0;
+        // count consecutive matvecs sharing x / type / k
+        size_t n = 1;
+        while (n < 3 && is(i + n, L_MATVEC) && q[i + n].b.buf == xbuf && q[i + n].a.buf->dtype == wt && q[i + n].a.shape[1] == k && vlen(q[i + n].b) == k) n++;
+        StreamArgs A = {};
+        A.k = (int)k;
+        A.exp_lut = dev->exp_lut;
+        size_t used = n;
+        // gate/up + silu + mul (llama2.rs:620-630)
+        if (n >= 2 && is(i + 2, L_SILU) && is(i + 3, L_MUL) && q[i + 2].a.buf == q[i].out && q[i + 3].a.buf == q[i].out && q[i + 3].b.buf == q[i + 1].out &&
+            q[i].a.shape[0] == q[i + 1].a.shape[0] && vlen(q[i + 3].b) == q[i].a.shape[0] && dead_after(q[i + 1].out, i + 4)) {
+            n = 2;
+            A.epilogue = 2;
+            used = 4;
+        } else if (n == 1 && is(i + 1, L_ADD) && q[i + 1].a.buf == m0.out && vlen(q[i + 1].b) == m0.a.shape[0] && q[i + 1].b.buf->dtype == CC_F32 && vcontig(q[i + 1].b)) {
+            A.epilogue = 1;                    // x = matvec + residual (llama2.rs:266,636)
+            A.residual = (const float*)q[i + 1].b.buf->plane[0];
+            used = 2;
+        } else if (n > 1 && is(i + n, L_SILU)) {
+            n = 1; used = 1;                   // do not swallow a gate/up pair we could not fuse as a pair
+        }
+        A.mats.n = (int)n;
+        for (size_t t = 0; t < n; t++) {
+            A.mats.qs[t] = q[i + t].a.buf->plane[0];
+            A.mats.d[t] = (const uint16_t*)q[i + t].a.buf->plane[1];
+            A.mats.out[t] = (float*)q[i + t].out->base;
+            A.mats.m[t] = (int)q[i + t].a.shape[0];
+        }
+        cc_device* d = dev;
+        void* act = lz->act[act_sel >= 0 ? act_sel : 1];
+        A.act = act;
+        if (act_sel < 0) {                     // plain quantise of x (matmul_vec.rs:37-40)
+            float* x = (float*)m0.b.buf->plane[0];
+            P.S(0x2002); P.SP(x); P.SP(act); P.S((uint64_t)k);
+            P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, nullptr, nullptr, 0.0f, k, act); });
+        }
+        P.S(0x2003); P.S(wt); P.S(k); P.S(A.epilogue); P.SP(A.residual); P.SP(act);
+        for (size_t t = 0; t < n; t++) { P.SP(A.mats.qs[t]); P.SP(A.mats.out[t]); P.S(A.mats.m[t]); }
+        P.steps.push_back([=](uint8_t*) { return cc_launch_matvec_stream(d, wt, A); });
+        for (size_t t = i; t < i + used; t++) q[t].done = true;
+        return used;
+    }
+
+    // ---- pattern: rope q,k + kv append + attention (llama2.rs:252-256, 541-590), n_batch == 1 -----------------------------------------------
+    size_t try_attention(size_t i, cc_buf** obuf) {
+        if (!(is(i, L_ROPE) && is(i + 1, L_ROPE) && is(i + 2, L_CONCAT) && is(i + 3, L_CONCAT) && is(i + 4, L_CONTIGUOUS) && is(i + 5, L_SCALE) &&
+              is(i + 6, L_BMM) && is(i + 7, L_SOFTMAX) && is(i + 8, L_BMM))) return 0;
+        const LOp &rq = q[i], &rk = q[i + 1], &ck = q[i + 2], &cv = q[i + 3], &ct = q[i + 4], &sc = q[i + 5], &b1 = q[i + 6], &sm = q[i + 7], &b2 = q[i + 8];
+        if (rq.a.ndim != 3 || rk.a.ndim != 3 || rq.a.shape[0] != 1 || rk.a.shape[0] != 1) return 0;
+        const int64_t n_heads = rq.a.shape[1], hd = rq.a.shape[2], n_kv = rk.a.shape[1];
+        if (rk.a.shape[2] != hd || (int)rq.f != CC_ROPE_LLAMA || (int)rk.f != CC_ROPE_LLAMA || rq.i0 != rk.i0 || rq.rows[0] != rk.rows[0]) return 0;
+        if (hd % 32 || hd > 256 || n_heads % n_kv) return 0;
+        cc_buf *qb = rq.a.buf, *kb = rk.a.buf, *kc = ck.a.buf, *vc = cv.a.buf, *vb = cv.b.buf;
+        if (ck.b.buf != kb || ck.i0 != 1 || cv.i0 != 1 || ck.a.ndim != 3 || cv.a.ndim != 3) return 0;
+        if (ck.a.shape[0] != n_kv || ck.a.shape[2] != hd || ck.a.strides[2] != 1 || ck.a.strides[1] != hd) return 0;
+        if (cv.a.shape[0] != n_kv || cv.a.shape[2] != hd || cv.a.strides[2] != 1 || cv.a.strides[1] != hd || cv.a.strides[0] != ck.a.strides[0]) return 0;
+        if (ck.a.shape[1] != cv.a.shape[1] || kc->dtype != vc->dtype) return 0;
+        const int64_t kv_len = ck.a.shape[1], seq_stride = ck.a.strides[0];
+        // rhs of the concats: [n_kv, 1, hd] views of the raw k / v rows
+        if (ck.b.ndim != 3 || ck.b.shape[0] != n_kv || ck.b.shape[1] != 1 || ck.b.shape[2] != hd || ck.b.strides[0] != hd || ck.b.strides[2] != 1) return 0;
+        if (cv.b.ndim != 3 || cv.b.shape[0] != n_kv || cv.b.shape[1] != 1 || cv.b.shape[2] != hd || cv.b.strides[0] != hd || cv.b.strides[2] != 1) return 0;
+        if (vb->dtype != CC_F32 || kb->dtype != CC_F32 || qb->dtype != CC_F32) return 0;
+        if (ct.a.buf != qb || sc.a.buf != ct.out || b1.a.buf != ct.out || b1.b.buf != kc || sm.a.buf != b1.out || b2.a.buf != b1.out || b2.b.buf != vc) return 0;
+        if (b1.b.shape[2] != kv_len + 1 || b1.b.strides[1] != 1 || b2.b.shape[1] != kv_len + 1 || b2.b.strides[2] != 1) return 0;
+        if (kv_len + 1 > seq_stride / hd) return 0;
+        // intermediates must not be observable afterwards
+        if (!dead_after(ct.out, i + 9) || !dead_after(b1.out, i + 9) || !dead_after(qb, i + 9) || !dead_after(kb, i + 9) || !dead_after(vb, i + 9)) return 0;
+        const int64_t pos = rq.i0, rope_dim = rq.rows[0];
+        if (rope_dim > hd || rope_dim % 2) return 0;
+        // RoPE table: host libm, identical calls to the reference (rope.rs:47-63); shared by all layers of this flush
+        if (rope_off == (size_t)-1 || rope_pos != pos || rope_hd != hd || this->rope_dim != rope_dim) {
+            std::vector<float> tab((size_t)rope_dim);
+            const int pairs = (int)rope_dim / 2;
+            float theta_scale = powf(10000.0f, -2.0f / (float)hd), theta = (float)pos;
+            for (int j = 0; j < pairs; j++) { tab[j] = cosf(theta); tab[pairs + j] = sinf(theta); theta *= theta_scale; }
+            rope_off = P.dyn_put(tab.data(), tab.size() * 4);
+            rope_pos = pos; rope_hd = (int)hd; this->rope_dim = (int)rope_dim;
+        }
+        int64_t dynv[2] = {pos, kv_len};
+        size_t dyn_off = P.dyn_put(dynv, sizeof(dynv));
+        AttnArgs A = {};
+        A.q = (const float*)qb->plane[0]; A.k = (const float*)kb->plane[0]; A.v = (const float*)vb->plane[0];
+        A.kcache = kc->plane[0]; A.vcache = vc->plane[0];
+        A.out = (float*)b2.out->base;
+        A.act_scratch = lz->act[1];
+        A.n_heads = (int)n_heads; A.n_kv = (int)n_kv; A.hd = (int)hd; A.rope_dim = (int)rope_dim;
+        A.max_len = (int)(seq_stride / hd); A.kv_f16 = kc->dtype == CC_F16;
+        A.seq_stride = seq_stride; A.scale = sc.f;
+        cc_device* d = dev;
+        size_t roff = rope_off;
+        P.S(0x2004); P.SP(A.q); P.SP(A.k); P.SP(A.v); P.SP(A.kcache); P.SP(A.vcache); P.SP(A.out); P.SP(A.act_scratch);
+        P.S(n_heads); P.S(n_kv); P.S(hd); P.S(rope_dim); P.S(seq_stride); P.S(A.kv_f16); uint32_t sb; memcpy(&sb, &A.scale, 4); P.S(sb); P.S(dyn_off); P.S(roff);
+        P.steps.push_back([=](uint8_t* dyn_dev) {
+            AttnArgs B = A;
+            B.dyn = (const int64_t*)(dyn_dev + dyn_off);
+            B.rope_tab = (const float*)(dyn_dev + roff);
+            return cc_launch_attn_decode(d, B);
+        });
+        *obuf = b2.out;
+        for (size_t t = i; t < i + 9; t++) q[t].done = true;
+        return 9;
+    }
+
+    // ---- pattern: embedding / row pick: COPY_ROWS with the row indices in dyn ---------------------------------------------------------------------
+    size_t try_copy_rows(size_t i) {
+        if (!is(i, L_COPY_ROWS)) return 0;
+        const LOp& op = q[i];
+        cc_device* d = dev;
+        size_t off = P.dyn_put(op.rows.data(), op.rows.size() * 8);
+        const cc_buf* src = op.b.buf;
+        void* dst = op.a.buf->plane[0];
+        int dt = op.a.buf->dtype, n = (int)op.rows.size();
+        int64_t cols = op.a.shape[op.a.ndim - 1];
+        P.S(0x2005); P.SP(src->plane[0]); P.SP(dst); P.S(dt); P.S(n); P.S(cols); P.S(off);
+        P.steps.push_back([=](uint8_t* dyn_dev) { return cc_launch_dequant_rows(d, src, (const int64_t*)(dyn_dev + off), n, cols, dst, dt); });
+        q[i].done = true;
+        return 1;
+    }
+
+    void run() {
+        size_t i = 0;
+        while (i < q.size()) {
+            if (q[i].done) { i++; continue; }
+            size_t used;
+            cc_buf* xb = nullptr;
+            if ((used = try_copy_rows(i))) { i += used; continue; }
+            if ((used = try_normq(i, 0, &xb))) {
+                i += used;
+                // every following group of matvecs on the normalised x reuses scratch 0
+                while (size_t u2 = try_stream(i, xb, 0)) i += u2;
+                continue;
+            }
+            if ((used = try_attention(i, &xb))) {
+                i += used;
+                if (size_t u2 = try_stream(i, xb, 1)) i += u2;      // wo consumes the quantised attention output
+                continue;
+            }
+            if (is(i, L_MATVEC) && q[i].b.buf->dtype == CC_F32 && (q[i].b.ndim == 1 || q[i].b.shape[0] == 1)) {
+                if ((used = try_stream(i, q[i].b.buf, -1))) { i += used; continue; }
+            }
+            fallback(i);
+            i++;
+        }
+    }
+};
+
+int cc_lazy_flush(cc_device* dev) {
+    LazyState* lz = dev->lz;
+    if (!lz || lz->q.empty()) return CC_OK;
+    lz->flushes++;
+    // scratch for the quantised activations (largest k in the queue)
+    int64_t max_k = 0;
+    for (auto& op : lz->q) if (op.kind == L_MATVEC) max_k = std::max<int64_t>(max_k, std::max<int64_t>(op.a.shape[1], 0));
+    for (auto& op : lz->q) if (op.kind == L_BMM) max_k = std::max<int64_t>(max_k, op.a.shape[0] * op.b.shape[2]);
+    size_t need = cc_act_bytes(CC_Q8_0, (max_k + 255) / 256 * 256) + 256;
+    int rc = CC_OK;
+    if (need > lz->act_cap) {
+        cudaStreamSynchronize(dev->stream);
+        for (int i = 0; i < 2; i++) { if (lz->act[i]) cudaFree(lz->act[i]); lz->act[i] = nullptr; }
+        size_t cap = 4096; while (cap < need) cap <<= 1;
+        for (int i = 0; i < 2; i++) if (cudaMalloc(&lz->act[i], cap) != cudaSuccess) return cc_fail(dev, CC_ERR_CUDA, "lazy: scratch alloc failed");
+        lz->act_cap = cap;
+    }
+    // eager matvec fallbacks use dev->act_scratch: make sure it is large enough BEFORE any capture
+    for (auto& op : lz->q) if (op.kind == L_MATVEC) {
+        int at = cc_partner_type(op.a.buf->dtype);
+        int64_t bb = op.b.ndim == 1 ? 1 : op.b.shape[0];
+        if (at != CC_F32 && (rc = cc_ensure_act_scratch(dev, cc_act_bytes(at, bb * op.a.shape[1])))) return rc;
+    }
+    Plan P;
+    Fuser F{dev, lz, lz->q, P};
+    F.run();
+    if (P.dyn.size() > lz->dyn_cap) P.cacheable = false;
+
+    auto run_steps = [&](uint8_t* dyn_dev) -> int {
+        for (auto& st : P.steps) { int r = st(dyn_dev); if (r) return r; }
+        return CC_OK;
+    };
+    // per-token values: pinned slot -> device block, as an ordinary stream copy in front of the launches / the graph
+    if (P.dyn.size() > lz->dyn_cap) rc = cc_fail(dev, CC_ERR_UNSUPPORTED, "lazy: dynamic argument block too large");
+    if (!rc && !P.dyn.empty()) {
+        const int s = lz->dyn_slot;
+        lz->dyn_slot ^= 1;
+        cudaEventSynchronize(lz->dyn_ev[s]);          // the copy that last read this slot (two flushes ago) is long done
+        memcpy(lz->dyn_host[s], P.dyn.data(), P.dyn.size());
+        if (cudaMemcpyAsync(lz->dyn_dev, lz->dyn_host[s], P.dyn.size(), cudaMemcpyHostToDevice, dev->stream) != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: dyn upload failed");
+        cudaEventRecord(lz->dyn_ev[s], dev->stream);
+    }
+    if (rc) {
+    } else if (!P.cacheable) {
+        lz->uncached++;
+        rc = run_steps(lz->dyn_dev);
+    } else {
+        P.S(P.dyn.size());
+        uint64_t key = hash_sig(P.sig);
+        auto it = lz->cache.find(key);
+        if (it == lz->cache.end()) {
+            lz->captures++;
+            uint64_t l0 = dev->launches;
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
+            if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
+            if (!rc) {
+                rc = run_steps(lz->dyn_dev);
+                e = cudaStreamEndCapture(dev->stream, &graph);
+                if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: end capture: %s", cudaGetErrorString(e));
+            }
+            GraphEntry ge;
+            if (!rc) {
+                e = cudaGraphInstantiate(&ge.exec, graph, 0);
+                if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: graph instantiate: %s", cudaGetErrorString(e));
+            }
+            if (graph) cudaGraphDestroy(graph);
+            if (!rc) {
+                ge.dyn_bytes = P.dyn.size();
+                ge.launches = dev->launches - l0;
+                dev->launches = l0;            // counted when the graph is launched
+                it = lz->cache.emplace(key, ge).first;
+            }
+        } else {
+            lz->graph_hits++;
+        }
+        if (!rc) {
+            cudaError_t e = cudaGraphLaunch(it->second.exec, dev->stream);
+            if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: graph launch: %s", cudaGetErrorString(e));
+            else dev->launches += it->second.launches;
+        }
+    }
+    // drop the queue's references, last op first (keeps pool pointer assignment identical from token to token)
+    std::vector<LOp> old;
+    old.swap(lz->q);
+    lz->qrefs.clear();
+    for (size_t t = old.size(); t-- > 0;) {
+        LOp& op = old[t];
+        if (op.out) cc_tensor_release(op.out);
+        if (op.b.buf) cc_tensor_release(op.b.buf);
+        if (op.a.buf) cc_tensor_release(op.a.buf);
+    }
+    return rc;
+}
+
+extern "C" CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out4) {
+    if (!dev || !dev->lz || !out4) return CC_ERR_ARG;
+    out4[0] = dev->lz->flushes; out4[1] = dev->lz->graph_hits; out4[2] = dev->lz->captures; out4[3] = dev->lz->uncached;
+    return CC_OK;
+}

@@ -127,6 +127,10 @@ __global__ void __launch_bounds__(MS_THREADS, MS_CTAS_PER_SM) matvec_stream_kern
     seg_load<TYPE>(buf0, l_ptr, 0, nb, GR, last_half_off, lane, U > 0);
     auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = vrow_ptr(++l_i); } };
     advance_load();
+    // programmatic dependent launch: let the next kernel be scheduled (it will prefetch ITS weights), then wait for
+    // the producer of our activation; everything above only touched immutable weights
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- 2. stage the quantised activation (global scratch -> shared), zero the padding ---------------------
     {
@@ -198,14 +202,26 @@ int cc_launch_matvec_stream(cc_device* dev, int type, const StreamArgs& A) {
     int64_t m_cat = A.epilogue == 2 ? A.mats.m[0] : (int64_t)A.mats.m[0] + (A.mats.n > 1 ? A.mats.m[1] : 0) + (A.mats.n > 2 ? A.mats.m[2] : 0);
     int64_t need = (m_cat + MS_WARPS - 1) / MS_WARPS;
     if (need < grid) grid = (int)(need > 0 ? need : 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(MS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = dev->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = dev->pdl ? 1 : 0;
+    cudaError_t e;
     if (type == CC_Q8_0) {
         if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(matvec_stream_kernel<CC_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        matvec_stream_kernel<CC_Q8_0><<<grid, MS_THREADS, smem, dev->stream>>>(A);
+        e = cudaLaunchKernelEx(&cfg, matvec_stream_kernel<CC_Q8_0>, A);
     } else {
         if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(matvec_stream_kernel<CC_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        matvec_stream_kernel<CC_Q4_0><<<grid, MS_THREADS, smem, dev->stream>>>(A);
+        e = cudaLaunchKernelEx(&cfg, matvec_stream_kernel<CC_Q4_0>, A);
     }
-    CC_LAUNCH_CHECK(dev);
+    if (e != cudaSuccess) return cc_fail(dev, CC_ERR_CUDA, "matvec_stream launch: %s", cudaGetErrorString(e));
+    dev->launches++;
     return CC_OK;
 }
 

@@ -96,6 +96,13 @@ class CudaTensorDevice:
         self.check(self.lib.cc_bench_timer_end(self.handle, C.byref(ms)))
         return float(ms.value)
     def launch_count(self): return int(self.lib.cc_device_launch_count(self.handle))
+    def flush(self): self.check(self.lib.cc_device_flush(self.handle))
+
+    def lazy_stats(self):
+        a = (C.c_uint64 * 4)()
+        if self.lib.cc_lazy_stats(self.handle, a) != capi.CC_OK:
+            return None
+        return {"flushes": a[0], "graph_replays": a[1], "graph_captures": a[2], "uncached": a[3]}
 
     def dump_debug_tensor(self, name):                              # cpu_device.rs:96-98
         n = C.c_size_t(0)

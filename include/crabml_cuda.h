@@ -81,6 +81,11 @@ CC_API int cc_device_create(const cc_device_options* opts, cc_device** out);
 CC_API void cc_device_destroy(cc_device* dev);
 CC_API const char* cc_last_error(cc_device* dev);          /* NULL dev: last creation error */
 CC_API int cc_device_synchronize(cc_device* dev);
+/* lazy mode: execute everything queued so far (asynchronously); a no-op in eager mode.  The runner calls it at the
+ * end of forward() when the logits are not exported. */
+CC_API int cc_device_flush(cc_device* dev);
+/* lazy mode statistics: {flushes, graph replays, graph captures, uncached (eager) flushes} */
+CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out4);
 /* counters: kernels launched by this library since creation (bench.py "gpu_launches") */
 CC_API uint64_t cc_device_launch_count(cc_device* dev);
 /* raw cudaStream_t of the device, for event timing by the caller */
