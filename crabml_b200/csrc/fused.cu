@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_decode_kernel(const float* __
         s_o[d] = o;
     }
     __syncthreads();
-    // Q8_0 quantisation of this head's hd outputs (hd/32 blocks), input of wo.matmul_vec
+    // Q8_0 quantisation of this head's hd outputs (hd/32 blocks), input of wo.matmul_vec -- only when blocks do not
+    // straddle heads (hd % 32 == 0); otherwise the consumer quantises the f32 row itself
+    if (act.qs != nullptr)
     for (int b = warp; b < (hd >> 5); b += AT_THREADS / 32) {
         float v = s_o[b * 32 + lane];
         float amax = warp_max(fabsf(v));
@@ -216,6 +218,7 @@ int cc_launch_attn_decode(cc_device* dev, const AttnArgs& a) {
     size_t smem = (size_t)(3 * a.hd + a.max_len + 8) * sizeof(float);
     CC_REQUIRE(dev, smem <= 200 * 1024, "attention: context %d too long for the single-pass kernel", a.max_len);
     ActQ8_0 act = cc_act_q8_0(a.act_scratch, (int64_t)a.n_heads * a.hd);
+    if (!a.act_scratch) act.qs = nullptr;
     cudaError_t e;
     if (a.kv_f16) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

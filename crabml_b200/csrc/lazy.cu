@@ -280,14 +280,15 @@ struct Fuser {
     }
 
     // ---- pattern: rope q,k + kv append + attention (llama2.rs:252-256, 541-590), n_batch == 1 -----------------------------------------------
-    size_t try_attention(size_t i, cc_buf** obuf) {
+    size_t try_attention(size_t i, cc_buf** obuf, bool* quantized) {
         if (!(is(i, L_ROPE) && is(i + 1, L_ROPE) && is(i + 2, L_CONCAT) && is(i + 3, L_CONCAT) && is(i + 4, L_CONTIGUOUS) && is(i + 5, L_SCALE) &&
               is(i + 6, L_BMM) && is(i + 7, L_SOFTMAX) && is(i + 8, L_BMM))) return 0;
         const LOp &rq = q[i], &rk = q[i + 1], &ck = q[i + 2], &cv = q[i + 3], &ct = q[i + 4], &sc = q[i + 5], &b1 = q[i + 6], &sm = q[i + 7], &b2 = q[i + 8];
         if (rq.a.ndim != 3 || rk.a.ndim != 3 || rq.a.shape[0] != 1 || rk.a.shape[0] != 1) return 0;
         const int64_t n_heads = rq.a.shape[1], hd = rq.a.shape[2], n_kv = rk.a.shape[1];
         if (rk.a.shape[2] != hd || (int)rq.f != CC_ROPE_LLAMA || (int)rk.f != CC_ROPE_LLAMA || rq.i0 != rk.i0 || rq.rows[0] != rk.rows[0]) return 0;
-        if (hd % 32 || hd > 256 || n_heads % n_kv) return 0;
+        if (hd > 256 || n_heads % n_kv) return 0;
+        *quantized = hd % 32 == 0;
         cc_buf *qb = rq.a.buf, *kb = rk.a.buf, *kc = ck.a.buf, *vc = cv.a.buf, *vb = cv.b.buf;
         if (ck.b.buf != kb || ck.i0 != 1 || cv.i0 != 1 || ck.a.ndim != 3 || cv.a.ndim != 3) return 0;
         if (ck.a.shape[0] != n_kv || ck.a.shape[2] != hd || ck.a.strides[2] != 1 || ck.a.strides[1] != hd) return 0;
@@ -320,7 +321,7 @@ struct Fuser {
         A.q = (const float*)qb->plane[0]; A.k = (const float*)kb->plane[0]; A.v = (const float*)vb->plane[0];
         A.kcache = kc->plane[0]; A.vcache = vc->plane[0];
         A.out = (float*)b2.out->base;
-        A.act_scratch = lz->act[1];
+        A.act_scratch = *quantized ? lz->act[1] : nullptr;
         A.n_heads = (int)n_heads; A.n_kv = (int)n_kv; A.hd = (int)hd; A.rope_dim = (int)rope_dim;
         A.max_len = (int)(seq_stride / hd); A.kv_f16 = kc->dtype == CC_F16;
         A.seq_stride = seq_stride; A.scale = sc.f;
@@ -368,9 +369,10 @@ struct Fuser {
                 while (size_t u2 = try_stream(i, xb, 0)) i += u2;
                 continue;
             }
-            if ((used = try_attention(i, &xb))) {
+            bool quantized = false;
+            if ((used = try_attention(i, &xb, &quantized))) {
                 i += used;
-                if (size_t u2 = try_stream(i, xb, 1)) i += u2;      // wo consumes the quantised attention output
+                if (size_t u2 = try_stream(i, xb, quantized ? 1 : -1)) i += u2;      // wo consumes the (quantised) attention output
                 continue;
             }
             if (is(i, L_MATVEC) && q[i].b.buf->dtype == CC_F32 && (q[i].b.ndim == 1 || q[i].b.shape[0] == 1)) {
