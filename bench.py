@@ -230,21 +230,24 @@ def run_b200(args, rank, world, local_rank):
     barrier()
 
     # ---- roofline of the dominant kernel: ffn_gate/ffn_up-shaped matvec over all layers' weights (>> L2) ----------
+    # (timed through an eager-mode device handle on the same GPU so that each matmul_vec is its own launch pair)
     m, k = conf.hidden_dim, conf.embedding_dim
-    x = CudaTensor.new(np.random.default_rng(1).standard_normal(k).astype(np.float32), [k], dev)
-    mats = weights["ffn_gate"] + weights["ffn_up"]
+    dev.synchronize()
+    edev = CudaTensorDevice(local_rank, lazy=False) if args.lazy else dev
+    x = CudaTensor.new(np.random.default_rng(1).standard_normal(k).astype(np.float32), [k], edev)
+    mats = [CudaTensor(wm.buf, wm.strider(), edev) for wm in weights["ffn_gate"] + weights["ffn_up"]]
     for wmat in mats[:4]:
         wmat.matmul_vec(x)
     reps = 3
-    dev.synchronize()
-    l0 = dev.launch_count()
-    dev.timer_begin()
+    edev.synchronize()
+    l0 = edev.launch_count()
+    edev.timer_begin()
     for _ in range(reps):
         for wmat in mats:
             wmat.matmul_vec(x)
-    mv_ms = dev.timer_end()
+    mv_ms = edev.timer_end()
     n_mv = reps * len(mats)
-    launches_per_mv = (dev.launch_count() - l0) / n_mv
+    launches_per_mv = (edev.launch_count() - l0) / n_mv
     mv_bytes = R.weight_bytes(wt, m, k)
     mv_gbs = mv_bytes / (mv_ms / n_mv * 1e-3) / 1e9
     peaks, peak_src = measured_peaks()
@@ -271,6 +274,7 @@ def run_b200(args, rank, world, local_rank):
                          "frac": mv_gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": mv_bytes,
                          "us_per_launch": mv_ms / n_mv * 1e3, "frac_of_8TBs_nominal": mv_gbs / 8000.0},
             "clocks": clocks,
+            "lazy_stats": dev.lazy_stats() if args.lazy else None,
         }
         if world == 1 and not args.no_cpu_baseline:
             tps, threads, sample, _ = cpu_reference_tokens_per_s(args.workload)
@@ -290,7 +294,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="llama2-7b-q8_0", choices=sorted(WORKLOADS))
     ap.add_argument("--start-pos", type=int, default=32, help="KV-cache length before the timed decode steps")
-    ap.add_argument("--lazy", type=int, default=0)
+    ap.add_argument("--lazy", type=int, default=1, help="1 = record+fuse+CUDA-graph replay (default), 0 = one launch per trait call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

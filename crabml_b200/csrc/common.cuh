@@ -9,6 +9,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -92,7 +93,7 @@ struct cc_device {
 
     // stream-ordered size-class pool for activations
     std::mutex mu;
-    std::unordered_map<size_t, std::vector<void*>> free_lists;
+    std::unordered_map<size_t, std::set<uintptr_t>> free_lists;   // per size class, ordered: allocation takes the LOWEST free address
     size_t pool_live_bytes = 0;
 
     // pinned staging for export / row indices

@@ -101,7 +101,7 @@ extern "C" CC_API void cc_device_destroy(cc_device* dev) {
     cudaStreamSynchronize(dev->stream);
     cc_lazy_destroy(dev);
     for (auto& kv : dev->free_lists)
-        for (void* p : kv.second) cudaFree(p);
+        for (uintptr_t p : kv.second) cudaFree((void*)p);
     if (dev->act_scratch) cudaFree(dev->act_scratch);
     if (dev->pinned) cudaFreeHost(dev->pinned);
     if (dev->dev_idx) cudaFree(dev->dev_idx);
@@ -155,8 +155,10 @@ int cc_pool_alloc(cc_device* dev, size_t bytes, void** out, size_t* cls) {
         std::lock_guard<std::mutex> g(dev->mu);
         auto& fl = dev->free_lists[c];
         if (!fl.empty()) {
-            *out = fl.back();
-            fl.pop_back();
+            // lowest address first: the buffer a call gets depends only on the SET of free buffers, not on the order in
+            // which they were released -> identical pointers token after token (lazy.cu hashes them into the graph key)
+            *out = (void*)*fl.begin();
+            fl.erase(fl.begin());
             return CC_OK;
         }
     }
@@ -166,7 +168,7 @@ int cc_pool_alloc(cc_device* dev, size_t bytes, void** out, size_t* cls) {
 }
 void cc_pool_free(cc_device* dev, void* p, size_t cls) {
     std::lock_guard<std::mutex> g(dev->mu);
-    dev->free_lists[cls].push_back(p);   // LIFO: deterministic pointer reuse for identical op sequences
+    dev->free_lists[cls].insert((uintptr_t)p);
 }
 
 int cc_new_activation(cc_device* dev, int64_t nelems, int dtype, bool zero, cc_buf** out) {
