@@ -221,10 +221,13 @@ def run_b200(args, rank, world, local_rank):
     toks = [(tok * 31 + 7 * i) % conf.vocab_size for i in range(K)]
     dev.synchronize(); barrier()
     launches1 = dev.launch_count()
-    dev.timer_begin()
+    st0 = dev.lazy_stats() if args.lazy else None
+    dev.timer_begin(); th0 = time.perf_counter()
     for i in range(K):
         runner.forward([toks[i]], pos, export=False); pos += 1
+    host_issue_ms = (time.perf_counter() - th0) * 1e3          # host time to record+submit K tokens (GPU runs behind)
     val_ms = max_over_ranks(dev.timer_end())
+    st1 = dev.lazy_stats() if args.lazy else None
     launches_val = dev.launch_count() - launches1
     clocks = sampler.stop()
     barrier()
@@ -275,6 +278,8 @@ def run_b200(args, rank, world, local_rank):
                          "us_per_launch": mv_ms / n_mv * 1e3, "frac_of_8TBs_nominal": mv_gbs / 8000.0},
             "clocks": clocks,
             "lazy_stats": dev.lazy_stats() if args.lazy else None,
+            "host_ms_per_step": {"issue_total": host_issue_ms / K,
+                                 **({k: (st1[k] - st0[k]) / 1e3 / K for k in ("host_us_record", "host_us_fuse", "host_us_submit")} if args.lazy else {})},
         }
         if world == 1 and not args.no_cpu_baseline:
             tps, threads, sample, _ = cpu_reference_tokens_per_s(args.workload)

@@ -206,7 +206,7 @@ struct AttnArgs {            // fused decode attention (fused.cu)
     int64_t seq_stride;
     float scale;
 };
-int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch);
+int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch, bool write_back);
 int cc_launch_attn_decode(cc_device* dev, const AttnArgs& a);
 struct LazyState;
 LazyState* cc_lazy_create(cc_device* dev);

@@ -14,32 +14,43 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 //   x <- (x / sqrt(sum(x^2)/n + eps)) * w   (optional)      rms_norm_inplace + mul_inplace (rms_norm.rs:32-47, llama2.rs:231-232,611-612)
 //   act <- quantize_q8_0(x)                                 buf_q8_0.rs:87-134 (what matmul_vec does first, matmul_vec.rs:37-40)
 // ---------------------------------------------------------------------------------------------------------------
-#define NQ_THREADS 1024
-__global__ void __launch_bounds__(NQ_THREADS) normq_kernel(float* x, float* orig, const float* norm_w, float eps, int n, ActQ8_0 act) {
-    __shared__ float s_red[32];
-    __shared__ float s_rms;
+#define NQ_THREADS 256
+#define NQ_MAX_CTAS 16
+// Every CTA recomputes sum(x^2) over the whole row (a few KB from L2, same order in every CTA -> identical rms), then
+// normalises / copies / quantises only its own slice of 32-element blocks.
+// write_back = 0 (x is dead after its consumers) is REQUIRED for a multi-CTA grid: no CTA may overwrite x while
+// another still sums it.
+__global__ void __launch_bounds__(NQ_THREADS) normq_kernel(float* x, float* orig, const float* norm_w, float eps, int n, ActQ8_0 act, int write_back) {
+    __shared__ float s_red[NQ_THREADS / 32];
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float rms = 1.0f;
     if (norm_w) {
         float ss = 0.0f;
-        for (int i = threadIdx.x; i < n; i += NQ_THREADS) { float v = x[i]; ss += v * v; }
+        const float4* x4 = (const float4*)x;
+        const int n4 = n >> 2;
+        for (int i0 = 0; i0 < n4; i0 += NQ_THREADS * 4) {           // 4 independent 16-byte loads in flight per thread
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { int i = i0 + j * NQ_THREADS + threadIdx.x; v[j] = i < n4 ? x4[i] : make_float4(0, 0, 0, 0); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        }
         ss = warp_sum(ss);
         if (lane == 0) s_red[warp] = ss;
         __syncthreads();
-        if (warp == 0) {
-            float t = s_red[lane];
-            t = warp_sum(t);
-            if (lane == 0) s_rms = sqrtf(t / (float)n + eps);
-        }
-        __syncthreads();
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NQ_THREADS / 32; w++) t += s_red[w];
+        rms = sqrtf(t / (float)n + eps);
     }
-    const float rms = norm_w ? s_rms : 1.0f;
     const int nb = n >> 5;
-    for (int b = warp; b < nb; b += NQ_THREADS / 32) {
+    const int gw = blockIdx.x * (NQ_THREADS / 32) + warp, tw = gridDim.x * (NQ_THREADS / 32);
+    for (int b = gw; b < nb; b += tw) {
         float v = x[b * 32 + lane];
         if (orig) orig[b * 32 + lane] = v;
-        if (norm_w) { v = (v / rms) * norm_w[b * 32 + lane]; x[b * 32 + lane] = v; }
+        if (norm_w) { v = (v / rms) * norm_w[b * 32 + lane]; if (write_back) x[b * 32 + lane] = v; }
         float amax = warp_max(fabsf(v));
         float d = amax / 127.0f;
         int q = __float2int_rz(v / d);
@@ -206,9 +217,14 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch) {
+int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch, bool write_back) {
     CC_REQUIRE(dev, n % 32 == 0, "normq: length %lld %% 32 != 0", (long long)n);
-    cudaError_t e = launch_pdl(normq_kernel, dim3(1), dim3(NQ_THREADS), 0, dev->stream, dev->pdl, x, orig, norm_w, eps, (int)n, cc_act_q8_0(act_scratch, n));
+    CC_REQUIRE(dev, n % 4 == 0, "normq: length %lld %% 4 != 0", (long long)n);
+    int ctas = (int)((n / 32 + NQ_THREADS / 32 - 1) / (NQ_THREADS / 32));
+    if (ctas > NQ_MAX_CTAS) ctas = NQ_MAX_CTAS;
+    if (ctas < 1 || (norm_w && write_back)) ctas = 1;
+    cudaError_t e = launch_pdl(normq_kernel, dim3(ctas), dim3(NQ_THREADS), 0, dev->stream, dev->pdl, x, orig, norm_w, eps, (int)n, cc_act_q8_0(act_scratch, n),
+                               write_back ? 1 : 0);
     if (e != cudaSuccess) return cc_fail(dev, CC_ERR_CUDA, "normq launch: %s", cudaGetErrorString(e));
     dev->launches++;
     return CC_OK;

@@ -15,6 +15,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <chrono>
 #include <functional>
 
 #include "common.cuh"
@@ -47,6 +48,7 @@ struct LazyState {
     size_t act_cap = 0;
     std::unordered_map<uint64_t, GraphEntry> cache;
     uint64_t flushes = 0, graph_hits = 0, captures = 0, uncached = 0;
+    uint64_t ns_record = 0, ns_fuse = 0, ns_submit = 0, n_ops = 0;      // host-side cost accounting
 };
 
 static LView mkview(const cc_view* v) {
@@ -90,11 +92,14 @@ static void hold(LazyState* lz, cc_buf* b) { if (b) { cc_tensor_retain(b); lz->q
 int cc_lazy_record(cc_device* dev, int kind, const cc_view* a, const cc_view* b, cc_buf* out, float f, int64_t i0, int64_t i1, int64_t i2,
                    const int64_t* rows, int n_rows) {
     LazyState* lz = dev->lz;
+    auto t0 = std::chrono::steady_clock::now();
     LOp op;
     op.kind = kind; op.a = mkview(a); op.b = mkview(b); op.out = out; op.f = f; op.i0 = i0; op.i1 = i1; op.i2 = i2;
     if (rows) op.rows.assign(rows, rows + n_rows);
     hold(lz, op.a.buf); hold(lz, op.b.buf); hold(lz, op.out);
     lz->q.push_back(std::move(op));
+    lz->n_ops++;
+    lz->ns_record += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     return CC_OK;
 }
 
@@ -221,8 +226,12 @@ struct Fuser {
         float eps = rn.f;
         void* act = lz->act[act_sel];
         cc_device* d = dev;
-        P.S(0x2001); P.SP(x); P.SP(og); P.SP(w); P.SP(act); P.S((uint64_t)n); uint32_t eb; memcpy(&eb, &eps, 4); P.S(eb);
-        P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, og, w, eps, n, act); });
+        // the normalised f32 row only has to be materialised if something other than the following matvecs reads it
+        size_t end = j + 2;
+        while (is(end, L_MATVEC) && q[end].b.buf == rn.a.buf) end++;
+        const bool write_back = !dead_after(rn.a.buf, end);
+        P.S(0x2001); P.SP(x); P.SP(og); P.SP(w); P.SP(act); P.S((uint64_t)n); uint32_t eb; memcpy(&eb, &eps, 4); P.S(eb); P.S(write_back);
+        P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, og, w, eps, n, act, write_back); });
         *xbuf = rn.a.buf;
         size_t used = (j + 2) - i;
         for (size_t t = i; t < i + used; t++) q[t].done = true;
@@ -270,7 +279,7 @@ struct Fuser {
         if (act_sel < 0) {                     // plain quantise of x (matmul_vec.rs:37-40)
             float* x = (float*)m0.b.buf->plane[0];
             P.S(0x2002); P.SP(x); P.SP(act); P.S((uint64_t)k);
-            P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, nullptr, nullptr, 0.0f, k, act); });
+            P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, nullptr, nullptr, 0.0f, k, act, false); });
         }
         P.S(0x2003); P.S(wt); P.S(k); P.S(A.epilogue); P.SP(A.residual); P.SP(act);
         for (size_t t = 0; t < n; t++) { P.SP(A.mats.qs[t]); P.SP(A.mats.out[t]); P.S(A.mats.m[t]); }
@@ -407,9 +416,12 @@ int cc_lazy_flush(cc_device* dev) {
         int64_t bb = op.b.ndim == 1 ? 1 : op.b.shape[0];
         if (at != CC_F32 && (rc = cc_ensure_act_scratch(dev, cc_act_bytes(at, bb * op.a.shape[1])))) return rc;
     }
+    auto t_f0 = std::chrono::steady_clock::now();
     Plan P;
     Fuser F{dev, lz, lz->q, P};
     F.run();
+    auto t_f1 = std::chrono::steady_clock::now();
+    lz->ns_fuse += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_f1 - t_f0).count();
     if (P.dyn.size() > lz->dyn_cap) P.cacheable = false;
 
     auto run_steps = [&](uint8_t* dyn_dev) -> int {
@@ -466,6 +478,7 @@ int cc_lazy_flush(cc_device* dev) {
             else dev->launches += it->second.launches;
         }
     }
+    lz->ns_submit += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_f1).count();
     // drop the queue's references, last op first (keeps pool pointer assignment identical from token to token)
     std::vector<LOp> old;
     old.swap(lz->q);
@@ -482,5 +495,6 @@ int cc_lazy_flush(cc_device* dev) {
 extern "C" CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out4) {
     if (!dev || !dev->lz || !out4) return CC_ERR_ARG;
     out4[0] = dev->lz->flushes; out4[1] = dev->lz->graph_hits; out4[2] = dev->lz->captures; out4[3] = dev->lz->uncached;
+    out4[4] = dev->lz->ns_record; out4[5] = dev->lz->ns_fuse; out4[6] = dev->lz->ns_submit; out4[7] = dev->lz->n_ops;
     return CC_OK;
 }

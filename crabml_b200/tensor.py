@@ -99,10 +99,11 @@ class CudaTensorDevice:
     def flush(self): self.check(self.lib.cc_device_flush(self.handle))
 
     def lazy_stats(self):
-        a = (C.c_uint64 * 4)()
+        a = (C.c_uint64 * 8)()
         if self.lib.cc_lazy_stats(self.handle, a) != capi.CC_OK:
             return None
-        return {"flushes": a[0], "graph_replays": a[1], "graph_captures": a[2], "uncached": a[3]}
+        return {"flushes": a[0], "graph_replays": a[1], "graph_captures": a[2], "uncached": a[3],
+                "host_us_record": a[4] / 1e3, "host_us_fuse": a[5] / 1e3, "host_us_submit": a[6] / 1e3, "ops": a[7]}
 
     def dump_debug_tensor(self, name):                              # cpu_device.rs:96-98
         n = C.c_size_t(0)

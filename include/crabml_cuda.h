@@ -84,8 +84,9 @@ CC_API int cc_device_synchronize(cc_device* dev);
 /* lazy mode: execute everything queued so far (asynchronously); a no-op in eager mode.  The runner calls it at the
  * end of forward() when the logits are not exported. */
 CC_API int cc_device_flush(cc_device* dev);
-/* lazy mode statistics: {flushes, graph replays, graph captures, uncached (eager) flushes} */
-CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out4);
+/* lazy mode statistics, 8 values: {flushes, graph replays, graph captures, uncached (eager) flushes,
+ * host ns spent recording, fusing, submitting, ops recorded} */
+CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out8);
 /* counters: kernels launched by this library since creation (bench.py "gpu_launches") */
 CC_API uint64_t cc_device_launch_count(cc_device* dev);
 /* raw cudaStream_t of the device, for event timing by the caller */
