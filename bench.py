@@ -188,7 +188,7 @@ def run_b200(args, rank, world, local_rank):
     cname, wt_name, ct_name = WORKLOADS[args.workload]
     conf = getattr(R, cname)
     wt, ct = TYPE_ID[wt_name], TYPE_ID[ct_name]
-    dev = CudaTensorDevice(local_rank, lazy=bool(args.lazy))
+    dev = CudaTensorDevice(local_rank, lazy=args.lazy)
     weights = R.synthetic_weights(dev, conf, wt, ct, seed=SEED)
     K, W = args.steps, args.warmup
     kv_len = min(conf.seq_len, args.start_pos + 2 * (W + K) + 8)
@@ -263,7 +263,7 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_step": val_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}-decode-synthetic", "weights": wt_name, "classifier": ct_name, "kv_cache": "f32",
-                       "start_pos": args.start_pos, "mode": "lazy-fused" if args.lazy else "eager (one launch per trait call)",
+                       "start_pos": args.start_pos, "mode": {0: "eager (one launch per trait call)", 1: "lazy: fused kernels, CUDA-graph replay", 2: "lazy: one persistent megakernel per token, CUDA-graph replay"}[args.lazy],
                        "multi_gpu": "independent replicas (row-sharded path: see DESIGN.md)" if world > 1 else "single GPU",
                        "l2_policy": f"weights streamed once per token ({bytes_per_token / 1e9:.2f} GB >> 126 MB L2): inputs larger than L2",
                        "weight_bytes_per_token": bytes_per_token,
@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="llama2-7b-q8_0", choices=sorted(WORKLOADS))
     ap.add_argument("--start-pos", type=int, default=32, help="KV-cache length before the timed decode steps")
-    ap.add_argument("--lazy", type=int, default=1, help="1 = record+fuse+CUDA-graph replay (default), 0 = one launch per trait call")
+    ap.add_argument("--lazy", type=int, default=2, help="2 = record+fuse, one persistent megakernel per token (default); 1 = fused kernels in a CUDA graph; 0 = one launch per trait call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -78,6 +78,7 @@ struct cc_device {
     bool lazy = false;
     bool exact = false;       // cc_device_options.exact_order
     bool pdl = true;          // launch fused-path kernels with programmatic dependent launch
+    bool mega = false;        // lazy mode 2: one persistent kernel per token (mega.cu)
     struct LazyState* lz = nullptr;   // non-null in lazy mode (lazy.cu)
     std::string last_error;
     uint64_t launches = 0;
@@ -206,6 +207,20 @@ struct AttnArgs {            // fused decode attention (fused.cu)
     int64_t seq_stride;
     float scale;
 };
+struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; int64_t cols; };
+// megakernel phase descriptor (mega.cu); built by lazy.cu
+enum { MK_NORMQ = 0, MK_MATVEC = 1, MK_ATTN = 2, MK_ROWS = 3 };
+struct MkPhase {
+    int type, wtype;
+    // NORMQ (and the output quantisation of ATTN)
+    float* x; float* orig; const float* norm_w; float eps; int n; ActQ8_0 act;
+    StreamArgs mv;                      // MATVEC
+    AttnArgs at;                        // ATTN
+    unsigned long long dyn_off, rope_off;   // ATTN {pos, kv_len} / ROWS row list ; RoPE table
+    DeqPlanes planes; int src_dtype, dst_dtype, n_rows, pad; long long cols; void* dst;   // ROWS
+};
+size_t cc_mega_smem_for_matvec(int type, int k);
+int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem);
 int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch, bool write_back);
 int cc_launch_attn_decode(cc_device* dev, const AttnArgs& a);
 struct LazyState;

@@ -72,6 +72,7 @@ extern "C" CC_API int cc_device_create(const cc_device_options* opts, cc_device*
     dev->debug_named_tensors = opts && opts->debug_named_tensors;
     dev->lazy = opts && opts->lazy;
     dev->exact = opts && opts->exact_order;
+    dev->mega = opts && opts->lazy >= 2;
 #define CREATE_CUDA(call)                                                                          \
     do { cudaError_t _e = (call); if (_e != cudaSuccess) { cc_fail(nullptr, CC_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); delete dev; return CC_ERR_CUDA; } } while (0)
     CREATE_CUDA(cudaSetDevice(ord));

@@ -34,7 +34,7 @@ struct LOp {
     bool done = false;
 };
 
-struct GraphEntry { cudaGraphExec_t exec = nullptr; size_t dyn_bytes = 0; uint64_t launches = 0; };
+struct GraphEntry { cudaGraphExec_t exec = nullptr; size_t dyn_bytes = 0; uint64_t launches = 0; MkPhase* phases_dev = nullptr; };
 
 struct LazyState {
     std::vector<LOp> q;
@@ -45,6 +45,7 @@ struct LazyState {
     uint8_t* dyn_dev = nullptr;
     size_t dyn_cap = 1 << 16;
     void* act[2] = {nullptr, nullptr};
+    unsigned* bar_dev = nullptr;     // megakernel grid barrier {count, generation}
     size_t act_cap = 0;
     std::unordered_map<uint64_t, GraphEntry> cache;
     uint64_t flushes = 0, graph_hits = 0, captures = 0, uncached = 0;
@@ -72,13 +73,15 @@ LazyState* cc_lazy_create(cc_device* dev) {
     for (int i = 0; i < 2; i++)
         if (cudaMallocHost(&lz->dyn_host[i], lz->dyn_cap) != cudaSuccess || cudaEventCreateWithFlags(&lz->dyn_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete lz; return nullptr; }
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
+    if (cudaMalloc(&lz->bar_dev, 64) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 64) != cudaSuccess) { delete lz; return nullptr; }
     return lz;
 }
 void cc_lazy_destroy(cc_device* dev) {
     LazyState* lz = dev->lz;
     if (!lz) return;
     for (auto& op : lz->q) { if (op.a.buf) cc_tensor_release(op.a.buf); if (op.b.buf) cc_tensor_release(op.b.buf); if (op.out) cc_tensor_release(op.out); }
-    for (auto& kv : lz->cache) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& kv : lz->cache) { cudaGraphExecDestroy(kv.second.exec); if (kv.second.phases_dev) cudaFree(kv.second.phases_dev); }
+    if (lz->bar_dev) cudaFree(lz->bar_dev);
     for (int i = 0; i < 2; i++) { if (lz->dyn_host[i]) cudaFreeHost(lz->dyn_host[i]); if (lz->dyn_ev[i]) cudaEventDestroy(lz->dyn_ev[i]); }
     if (lz->dyn_dev) cudaFree(lz->dyn_dev);
     for (int i = 0; i < 2; i++) if (lz->act[i]) cudaFree(lz->act[i]);
@@ -109,6 +112,9 @@ struct Plan {
     std::vector<uint8_t> dyn;
     std::vector<std::function<int(uint8_t* dyn_dev)>> steps;
     bool cacheable = true;
+    std::vector<MkPhase> phases;     // megakernel form of the same plan (valid while mega_ok)
+    bool mega_ok = true;
+    size_t mega_smem = 1024;
     void S(uint64_t v) { sig.push_back(v); }
     void SP(const void* p) { sig.push_back((uint64_t)(uintptr_t)p); }
     size_t dyn_put(const void* p, size_t n) {
@@ -145,6 +151,7 @@ struct Fuser {
 
     // ---- eager fallback for one op -----------------------------------------------------------------------------
     void fallback(size_t i) {
+        P.mega_ok = false;
         LOp op = q[i];       // copy: lambdas outlive the queue only until flush ends, but keep them self-contained
         cc_device* d = dev;
         P.S(0x1000 + op.kind); P.SP(op.a.buf ? op.a.buf->plane[0] : nullptr); P.SP(op.b.buf ? op.b.buf->plane[0] : nullptr);
@@ -232,6 +239,8 @@ struct Fuser {
         const bool write_back = !dead_after(rn.a.buf, end);
         P.S(0x2001); P.SP(x); P.SP(og); P.SP(w); P.SP(act); P.S((uint64_t)n); uint32_t eb; memcpy(&eb, &eps, 4); P.S(eb); P.S(write_back);
         P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, og, w, eps, n, act, write_back); });
+        if (write_back) P.mega_ok = false;       // a grid-wide normq cannot update x in place (see fused.cu)
+        { MkPhase ph = {}; ph.type = MK_NORMQ; ph.x = x; ph.orig = og; ph.norm_w = w; ph.eps = eps; ph.n = (int)n; ph.act = cc_act_q8_0(act, n); P.phases.push_back(ph); }
         *xbuf = rn.a.buf;
         size_t used = (j + 2) - i;
         for (size_t t = i; t < i + used; t++) q[t].done = true;
@@ -280,10 +289,12 @@ struct Fuser {
             float* x = (float*)m0.b.buf->plane[0];
             P.S(0x2002); P.SP(x); P.SP(act); P.S((uint64_t)k);
             P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, nullptr, nullptr, 0.0f, k, act, false); });
+            { MkPhase ph = {}; ph.type = MK_NORMQ; ph.x = x; ph.n = (int)k; ph.act = cc_act_q8_0(act, k); P.phases.push_back(ph); }
         }
         P.S(0x2003); P.S(wt); P.S(k); P.S(A.epilogue); P.SP(A.residual); P.SP(act);
         for (size_t t = 0; t < n; t++) { P.SP(A.mats.qs[t]); P.SP(A.mats.out[t]); P.S(A.mats.m[t]); }
         P.steps.push_back([=](uint8_t*) { return cc_launch_matvec_stream(d, wt, A); });
+        { MkPhase ph = {}; ph.type = MK_MATVEC; ph.wtype = wt; ph.mv = A; P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_matvec(wt, (int)k)); }
         for (size_t t = i; t < i + used; t++) q[t].done = true;
         return used;
     }
@@ -344,6 +355,8 @@ struct Fuser {
             B.rope_tab = (const float*)(dyn_dev + roff);
             return cc_launch_attn_decode(d, B);
         });
+        { MkPhase ph = {}; ph.type = MK_ATTN; ph.at = A; ph.dyn_off = dyn_off; ph.rope_off = roff; ph.act = cc_act_q8_0(lz->act[1], n_heads * hd);
+          P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, (size_t)(3 * hd + A.max_len + 8) * 4); }
         *obuf = b2.out;
         for (size_t t = i; t < i + 9; t++) q[t].done = true;
         return 9;
@@ -361,6 +374,8 @@ struct Fuser {
         int64_t cols = op.a.shape[op.a.ndim - 1];
         P.S(0x2005); P.SP(src->plane[0]); P.SP(dst); P.S(dt); P.S(n); P.S(cols); P.S(off);
         P.steps.push_back([=](uint8_t* dyn_dev) { return cc_launch_dequant_rows(d, src, (const int64_t*)(dyn_dev + off), n, cols, dst, dt); });
+        { MkPhase ph = {}; ph.type = MK_ROWS; ph.dyn_off = off; for (int t = 0; t < CC_MAX_PLANES; t++) ph.planes.p[t] = src->plane[t];
+          ph.planes.cols = src->cols > 0 ? src->cols : cols; ph.src_dtype = src->dtype; ph.dst_dtype = dt; ph.n_rows = n; ph.cols = cols; ph.dst = dst; P.phases.push_back(ph); }
         q[i].done = true;
         return 1;
     }
@@ -450,14 +465,20 @@ int cc_lazy_flush(cc_device* dev) {
             lz->captures++;
             uint64_t l0 = dev->launches;
             cudaGraph_t graph = nullptr;
-            cudaError_t e = cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
-            if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
+            GraphEntry ge;
+            const bool use_mega = dev->mega && P.mega_ok && !P.phases.empty();
+            if (use_mega) {       // phase table lives in device memory for the lifetime of the graph
+                if (cudaMalloc(&ge.phases_dev, P.phases.size() * sizeof(MkPhase)) != cudaSuccess ||
+                    cudaMemcpy(ge.phases_dev, P.phases.data(), P.phases.size() * sizeof(MkPhase), cudaMemcpyHostToDevice) != cudaSuccess)
+                    rc = cc_fail(dev, CC_ERR_CUDA, "lazy: phase table upload failed");
+            }
+            cudaError_t e = rc ? cudaSuccess : cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
+            if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
             if (!rc) {
-                rc = run_steps(lz->dyn_dev);
+                rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);
                 if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: end capture: %s", cudaGetErrorString(e));
             }
-            GraphEntry ge;
             if (!rc) {
                 e = cudaGraphInstantiate(&ge.exec, graph, 0);
                 if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: graph instantiate: %s", cudaGetErrorString(e));

@@ -1,0 +1,410 @@
+// mega.cu -- one persistent kernel per token ("megakernel") for the fused decode path.
+//
+// Why: profiles/r01c/r01d -- on B200 a kernel boundary costs ~4-5 us for a full-GPU streaming kernel (drain, launch
+// latency, ramp-up) and ~2-3 us for a tiny one; a fused Llama-2-7B token still has ~260 of them (~1 ms), as much as the
+// 1.05 ms the weights need at HBM speed.  Here the whole token is ONE launch of 2 CTAs per SM that walks a table of
+// phases (built by lazy.cu from the recorded trait calls) separated by grid-wide barriers (~1 us each):
+//     NORMQ   [dup] + rms_norm * w + Q8_0 quantisation          (slices of blocks per CTA, rms recomputed per CTA)
+//     MATVEC  streaming matvec over 1-3 matrices + epilogue     (same body as matvec_stream.cu)
+//     ATTN    rope + KV append + attention + output quantise    (one CTA per head)
+//     ROWS    copy_rows_from (embedding row dequantisation)
+// Data written by one CTA and read by another in a later phase is always read with ld.global.cg (L2), never through
+// the non-coherent L1.  All CTAs execute the same number of barriers.
+#include "common.cuh"
+#include "dequant.cuh"
+
+#define MK_THREADS 256
+#define MK_WARPS 8
+#define MK_CTAS_PER_SM 2
+#define MK_SEG 4
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// sense-free generation barrier: bar[0] = arrival count, bar[1] = generation
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned gen = ld_acquire_u32(&bar[1]);
+        __threadfence();
+        const unsigned prev = atomicAdd(&bar[0], 1u);
+        if (prev == nblocks - 1) {
+            bar[0] = 0;
+            __threadfence();
+            st_release_u32(&bar[1], gen + 1);
+        } else {
+            while (ld_acquire_u32(&bar[1]) == gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
+
+// ---- NORMQ phase (fused.cu normq_kernel, grid-wide) -----------------------------------------------------------------
+__device__ void phase_normq(const MkPhase& ph, float* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = ph.n;
+    float* x = ph.x;
+    float rms = 1.0f;
+    if (ph.norm_w) {
+        float ss = 0.0f;
+        const float4* x4 = (const float4*)x;
+        const int n4 = n >> 2;
+        for (int i0 = 0; i0 < n4; i0 += MK_THREADS * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { int i = i0 + j * MK_THREADS + threadIdx.x; v[j] = i < n4 ? __ldcg(x4 + i) : make_float4(0, 0, 0, 0); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) s_red[warp] = ss;
+        __syncthreads();
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < MK_WARPS; w++) t += s_red[w];
+        rms = sqrtf(t / (float)n + ph.eps);
+        __syncthreads();
+    }
+    ActQ8_0 act = ph.act;
+    const int nb = n >> 5;
+    const int gw = blockIdx.x * MK_WARPS + warp, tw = gridDim.x * MK_WARPS;
+    for (int b = gw; b < nb; b += tw) {
+        float v = ldcg_f(x + b * 32 + lane);
+        if (ph.orig) ph.orig[b * 32 + lane] = v;
+        if (ph.norm_w) v = (v / rms) * ph.norm_w[b * 32 + lane];
+        float amax = warp_max(fabsf(v));
+        float d = amax / 127.0f;
+        int q = __float2int_rz(v / d);
+        act.qs[b * 32 + lane] = (int8_t)q;
+        int s = warp_sum_i(q);
+        if (lane == 0) { act.d[b] = __half2float(__float2half_rn(d)); act.isum[b] = s; }
+    }
+}
+
+// ---- MATVEC phase: the body of matvec_stream_kernel (see matvec_stream.cu for the design notes) -------------------------
+__device__ __forceinline__ int mk_dp16(const int4& w, const int4& a) {
+    return __dp4a(w.x, a.x, __dp4a(w.y, a.y, __dp4a(w.z, a.z, __dp4a(w.w, a.w, 0))));
+}
+template <int TYPE> struct MkSeg;
+template <> struct MkSeg<CC_Q8_0> { int4 a[MK_SEG], b[MK_SEG]; uint16_t s[MK_SEG]; };
+template <> struct MkSeg<CC_Q4_0> { int4 a[MK_SEG]; uint16_t s[MK_SEG]; };
+struct MkRowPtr { const uint8_t* q; const uint16_t* d; };
+
+template <int TYPE>
+__device__ __forceinline__ void mk_seg_load(MkSeg<TYPE>& S, const MkRowPtr& p, int seg, int nb, int GR, int last_half_off, int lane, bool valid) {
+    constexpr int GB = TYPE == CC_Q8_0 ? 1024 : 512;
+    const uint8_t* q = p.q + (size_t)seg * (MK_SEG * GB);
+    const uint16_t* d = p.d + seg * (MK_SEG * 32);
+#pragma unroll
+    for (int g = 0; g < MK_SEG; g++) {
+        const int gi = seg * MK_SEG + g;
+        const bool on = valid && (gi * 32 + lane < nb);
+        if constexpr (TYPE == CC_Q8_0) {
+            const int hoff = gi == GR - 1 ? last_half_off : 512;
+            if (on) { S.a[g] = ld_stream_16(q + g * GB); S.b[g] = ld_stream_16(q + g * GB + hoff); S.s[g] = d[g * 32]; }
+            else { S.a[g] = make_int4(0, 0, 0, 0); S.b[g] = S.a[g]; S.s[g] = 0; }
+        } else {
+            if (on) { S.a[g] = ld_stream_16(q + g * GB); S.s[g] = d[g * 32]; }
+            else { S.a[g] = make_int4(0, 0, 0, 0); S.s[g] = 0; }
+        }
+    }
+}
+template <int TYPE>
+__device__ __forceinline__ float mk_seg_dot(const MkSeg<TYPE>& S, int seg, const int4* aq_l, const float* ad_l, const int* as_l) {
+    float acc = 0.0f;
+    const int4* aq = aq_l + seg * (MK_SEG * 64);
+    const float* ad = ad_l + seg * (MK_SEG * 32);
+#pragma unroll
+    for (int g = 0; g < MK_SEG; g++) {
+        if constexpr (TYPE == CC_Q8_0) {
+            int sumi = mk_dp16(S.a[g], aq[g * 64]) + mk_dp16(S.b[g], aq[g * 64 + 1]);
+            acc += (float)sumi * h2f_bits(S.s[g]) * ad[g * 32];
+        } else {
+            const int4 w = S.a[g];
+            int4 lo = make_int4(w.x & 0x0F0F0F0F, w.y & 0x0F0F0F0F, w.z & 0x0F0F0F0F, w.w & 0x0F0F0F0F);
+            int4 hi = make_int4((w.x >> 4) & 0x0F0F0F0F, (w.y >> 4) & 0x0F0F0F0F, (w.z >> 4) & 0x0F0F0F0F, (w.w >> 4) & 0x0F0F0F0F);
+            int sumi = mk_dp16(lo, aq[g * 64]) + mk_dp16(hi, aq[g * 64 + 1]) - 8 * as_l[(seg * MK_SEG + g) * 32];
+            acc += (float)sumi * h2f_bits(S.s[g]) * ad[g * 32];
+        }
+    }
+    return acc;
+}
+
+template <int TYPE>
+__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut) {
+    const StreamArgs& A = ph.mv;
+    const int k = A.k, nb = k >> 5, GR = (nb + 31) >> 5, NSEG = (GR + MK_SEG - 1) / MK_SEG;
+    const int nbp = NSEG * MK_SEG * 32;
+    int8_t* s_q = (int8_t*)smem;
+    float* s_d = (float*)(smem + (size_t)nbp * 32);
+    int* s_s = (int*)(smem + (size_t)nbp * 32 + (size_t)nbp * 4);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * MK_WARPS + warp, TW = gridDim.x * MK_WARPS;
+    const StreamMats& M = A.mats;
+    const bool pair = A.epilogue == 2;
+    const int m_cat = pair ? M.m[0] : M.m[0] + (M.n > 1 ? M.m[1] : 0) + (M.n > 2 ? M.m[2] : 0);
+    const int n_rows = gw < m_cat ? (m_cat - gw + TW - 1) / TW : 0;
+    const int n_vrows = pair ? 2 * n_rows : n_rows;
+    const int U = n_vrows * NSEG;
+    const int last_half_off = 16 * (nb - 32 * (GR - 1));
+    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
+
+    auto vrow_ptr = [&](int i) -> MkRowPtr {
+        int mat = 0, r;
+        if (pair) { mat = i & 1; r = gw + (i >> 1) * TW; }
+        else {
+            r = gw + i * TW;
+            if (M.n > 1 && r >= M.m[0]) { r -= M.m[0]; mat = 1; if (M.n > 2 && r >= M.m[1]) { r -= M.m[1]; mat = 2; } }
+        }
+        const uint8_t* q0 = mat == 0 ? M.qs[0] : mat == 1 ? M.qs[1] : M.qs[2];
+        const uint16_t* d0 = mat == 0 ? M.d[0] : mat == 1 ? M.d[1] : M.d[2];
+        MkRowPtr p;
+        p.q = q0 + (size_t)r * nb * BB + lane * 16;
+        p.d = d0 + (size_t)r * nb + lane;
+        return p;
+    };
+    MkSeg<TYPE> buf0, buf1;
+    int l_i = 0, l_seg = 0;
+    MkRowPtr l_ptr = vrow_ptr(0);
+    mk_seg_load<TYPE>(buf0, l_ptr, 0, nb, GR, last_half_off, lane, U > 0);
+    auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = vrow_ptr(++l_i); } };
+    advance_load();
+    {   // stage the quantised activation (written by other CTAs in the previous phase: L2 loads)
+        const uint8_t* act = (const uint8_t*)A.act;
+        const int4* gq = (const int4*)act;
+        int4* sq4 = (int4*)s_q;
+        for (int i = threadIdx.x; i < nbp * 2; i += MK_THREADS) sq4[i] = i < nb * 2 ? __ldcg(gq + i) : make_int4(0, 0, 0, 0);
+        const float* gd = (const float*)(act + ((k + 15) & ~15));
+        const int* gs = (const int*)(act + ((k + 15) & ~15) + ((nb * 4 + 15) & ~15));
+        for (int i = threadIdx.x; i < nbp; i += MK_THREADS) {
+            s_d[i] = i < nb ? __ldcg(gd + i) : 0.0f;
+            if constexpr (TYPE == CC_Q4_0) s_s[i] = i < nb ? __ldcg(gs + i) : 0;
+        }
+    }
+    __syncthreads();
+    const int4* aq_l = (const int4*)s_q + 2 * lane;
+    const float* ad_l = s_d + lane;
+    const int* as_l = s_s + lane;
+    float acc = 0.0f, first = 0.0f;
+    int c_i = 0, c_seg = 0;
+    auto finish_segment = [&]() {
+        if (++c_seg < NSEG) return;
+        c_seg = 0;
+        float r = warp_sum(acc);
+        acc = 0.0f;
+        const int i = c_i++;
+        if (pair) {
+            if ((i & 1) == 0) { first = r; return; }
+            if (lane == 0) {
+                float g = first;
+                float nexp = h2f_bits(exp_lut[f2h_bits(-g)]);
+                M.out[0][gw + (i >> 1) * TW] = (g / (1.0f + nexp)) * r;
+            }
+            return;
+        }
+        if (lane == 0) {
+            int mat = 0, rr = gw + i * TW;
+            if (M.n > 1 && rr >= M.m[0]) { rr -= M.m[0]; mat = 1; if (M.n > 2 && rr >= M.m[1]) { rr -= M.m[1]; mat = 2; } }
+            if (A.epilogue == 1) r = r + ldcg_f(A.residual + rr);
+            float* o = mat == 0 ? M.out[0] : mat == 1 ? M.out[1] : M.out[2];
+            o[rr] = r;
+        }
+    };
+    for (int u = 0; u < U; u += 2) {
+        mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, last_half_off, lane, u + 1 < U);
+        advance_load();
+        acc += mk_seg_dot<TYPE>(buf0, c_seg, aq_l, ad_l, as_l);
+        finish_segment();
+        if (u + 1 >= U) break;
+        mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, last_half_off, lane, u + 2 < U);
+        advance_load();
+        acc += mk_seg_dot<TYPE>(buf1, c_seg, aq_l, ad_l, as_l);
+        finish_segment();
+    }
+}
+
+// ---- ATTN phase: body of fused.cu attn_decode_kernel, heads dealt to CTAs ----------------------------------------------
+template <bool KV_F16>
+__device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uint8_t* dyn, const uint16_t* exp_lut) {
+    const AttnArgs& a = ph.at;
+    const int n_heads = a.n_heads, n_kv = a.n_kv, hd = a.hd, rope_dim = a.rope_dim;
+    const int64_t seq_stride = a.seq_stride;
+    const int64_t* dynv = (const int64_t*)(dyn + ph.dyn_off);
+    const float* rope_tab = (const float*)(dyn + ph.rope_off);
+    const int kv_len = (int)dynv[1], L = kv_len + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* s_q = sm; float* s_k = sm + hd; float* s_v = sm + 2 * hd; float* s_p = sm + 3 * hd;
+    const int pairs = rope_dim >> 1;
+    for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
+        const int g = KV_F16 ? h / (n_heads / n_kv) : h % n_kv;
+        for (int i = threadIdx.x; i < hd; i += MK_THREADS) {
+            float qv, kvv;
+            if (i < rope_dim) {
+                const int j = i >> 1;
+                const float c = rope_tab[j], s = rope_tab[pairs + j];
+                const float q0 = ldcg_f(a.q + h * hd + 2 * j), q1 = ldcg_f(a.q + h * hd + 2 * j + 1);
+                const float k0 = ldcg_f(a.k + g * hd + 2 * j), k1 = ldcg_f(a.k + g * hd + 2 * j + 1);
+                qv = (i & 1) ? q0 * s + q1 * c : q0 * c - q1 * s;
+                kvv = (i & 1) ? k0 * s + k1 * c : k0 * c - k1 * s;
+            } else {
+                qv = ldcg_f(a.q + h * hd + i);
+                kvv = ldcg_f(a.k + g * hd + i);
+            }
+            s_q[i] = qv * a.scale;
+            s_k[i] = kvv;
+            s_v[i] = ldcg_f(a.v + g * hd + i);
+        }
+        __syncthreads();
+        const bool owner = KV_F16 ? (h % (n_heads / n_kv) == 0) : (h < n_kv);
+        if (owner) {
+            for (int i = threadIdx.x; i < hd; i += MK_THREADS) {
+                const int64_t off = (int64_t)g * seq_stride + (int64_t)kv_len * hd + i;
+                if (KV_F16) { ((__half*)a.kcache)[off] = __float2half_rn(s_k[i]); ((__half*)a.vcache)[off] = __float2half_rn(s_v[i]); }
+                else { ((float*)a.kcache)[off] = s_k[i]; ((float*)a.vcache)[off] = s_v[i]; }
+            }
+        }
+        for (int s = warp; s < L; s += MK_WARPS) {
+            float acc = 0.0f;
+            if (s < kv_len) {
+                if (KV_F16) {
+                    const __half* kr = (const __half*)a.kcache + (int64_t)g * seq_stride + (int64_t)s * hd;
+                    for (int i = lane; i < hd; i += 32) acc += __half2float(__float2half_rn(s_q[i])) * __half2float(kr[i]);
+                } else {
+                    const float* kr = (const float*)a.kcache + (int64_t)g * seq_stride + (int64_t)s * hd;
+                    for (int i = lane; i < hd; i += 32) acc += s_q[i] * kr[i];
+                }
+            } else {
+                for (int i = lane; i < hd; i += 32) {
+                    if (KV_F16) acc += __half2float(__float2half_rn(s_q[i])) * __half2float(__float2half_rn(s_k[i]));
+                    else acc += s_q[i] * s_k[i];
+                }
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) s_p[s] = acc;
+        }
+        __syncthreads();
+        float m = -INFINITY;
+        for (int s = threadIdx.x; s < L; s += MK_THREADS) m = fmaxf(m, s_p[s]);
+        m = warp_max(m);
+        if (lane == 0) s_red[warp] = m;
+        __syncthreads();
+        m = s_red[0];
+#pragma unroll
+        for (int w = 1; w < MK_WARPS; w++) m = fmaxf(m, s_red[w]);
+        __syncthreads();
+        float sum = 0.0f;
+        for (int s = threadIdx.x; s < L; s += MK_THREADS) {
+            float e = h2f_bits(exp_lut[f2h_bits(s_p[s] - m)]);
+            s_p[s] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) s_red[warp] = sum;
+        __syncthreads();
+        sum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < MK_WARPS; w++) sum += s_red[w];
+        for (int s = threadIdx.x; s < L; s += MK_THREADS) s_p[s] = s_p[s] / sum;
+        __syncthreads();
+        float* s_o = s_k;
+        for (int d = threadIdx.x; d < hd; d += MK_THREADS) {
+            float o;
+            if (KV_F16) {
+                const __half* vb = (const __half*)a.vcache + (int64_t)g * seq_stride + d;
+                __half acc = __float2half_rn(0.0f);
+                for (int s = 0; s < kv_len; s++) acc = __hadd(acc, __hmul(vb[(int64_t)s * hd], __float2half_rn(s_p[s])));
+                acc = __hadd(acc, __hmul(__float2half_rn(s_v[d]), __float2half_rn(s_p[kv_len])));
+                o = __half2float(acc);
+            } else {
+                const float* vb = (const float*)a.vcache + (int64_t)g * seq_stride + d;
+                float acc = 0.0f;
+                for (int s = 0; s < kv_len; s++) acc += s_p[s] * vb[(int64_t)s * hd];
+                acc += s_p[kv_len] * s_v[d];
+                o = acc;
+            }
+            a.out[h * hd + d] = o;
+            s_o[d] = o;
+        }
+        __syncthreads();
+        if (a.act_scratch) {
+            ActQ8_0 act = ph.act;
+            for (int b = warp; b < (hd >> 5); b += MK_WARPS) {
+                float v = s_o[b * 32 + lane];
+                float amax = warp_max(fabsf(v));
+                float d = amax / 127.0f;
+                int qq = __float2int_rz(v / d);
+                const int gb = h * (hd >> 5) + b;
+                act.qs[gb * 32 + lane] = (int8_t)qq;
+                int ss = warp_sum_i(qq);
+                if (lane == 0) { act.d[gb] = __half2float(__float2half_rn(d)); act.isum[gb] = ss; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- ROWS phase: copy_rows_from with the row indices in dyn (embedding lookup / row pick) -----------------------------------
+__device__ void phase_rows(const MkPhase& ph, const uint8_t* dyn) {
+    const int64_t* rows = (const int64_t*)(dyn + ph.dyn_off);
+    const int64_t total = (int64_t)ph.n_rows * ph.cols;
+    for (int64_t i = (int64_t)blockIdx.x * MK_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * MK_THREADS) {
+        const int64_t r = i / ph.cols, c = i - r * ph.cols;
+        const int64_t e = rows[r] * ph.cols + c;
+        float v;
+        if (ph.src_dtype == CC_F32) v = __ldcg((const float*)ph.planes.p[0] + e);
+        else if (ph.src_dtype == CC_F16) v = __half2float(((const __half*)ph.planes.p[0])[e]);
+        else v = dequant_elem(ph.src_dtype, ph.planes, e);
+        if (ph.dst_dtype == CC_F32) ((float*)ph.dst)[i] = v; else ((__half*)ph.dst)[i] = __float2half_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
+                                                                         unsigned* bar, const uint16_t* exp_lut) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ float s_red[MK_WARPS];
+    __shared__ MkPhase s_ph;
+    for (int p = 0; p < n_phases; p++) {
+        // one copy of the descriptor per CTA
+        {
+            const int* src = (const int*)(phases + p);
+            int* dst = (int*)&s_ph;
+            for (int i = threadIdx.x; i < (int)(sizeof(MkPhase) / 4); i += MK_THREADS) dst[i] = src[i];
+        }
+        __syncthreads();
+        switch (s_ph.type) {
+        case MK_NORMQ: phase_normq(s_ph, s_red); break;
+        case MK_MATVEC:
+            if (s_ph.wtype == CC_Q8_0) phase_matvec<CC_Q8_0>(s_ph, smem, exp_lut); else phase_matvec<CC_Q4_0>(s_ph, smem, exp_lut);
+            break;
+        case MK_ATTN:
+            if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)smem, s_red, dyn, exp_lut); else phase_attn<false>(s_ph, (float*)smem, s_red, dyn, exp_lut);
+            break;
+        case MK_ROWS: phase_rows(s_ph, dyn); break;
+        }
+        if (p + 1 < n_phases) grid_barrier(bar, gridDim.x);
+    }
+}
+
+size_t cc_mega_smem_for_matvec(int type, int k) {
+    size_t nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
+    return nbp * 32 + nbp * 4 + (type == CC_Q4_0 ? nbp * 4 : 0);
+}
+
+int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem) {
+    int max_ctas_per_sm = 0;
+    if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, mega_kernel, MK_THREADS, smem));
+    CC_REQUIRE(dev, max_ctas_per_sm >= 1, "megakernel does not fit on an SM");
+    int per_sm = max_ctas_per_sm < MK_CTAS_PER_SM ? max_ctas_per_sm : MK_CTAS_PER_SM;
+    int grid = dev->sm_count * per_sm;          // all CTAs co-resident: required by the grid barrier
+    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut);
+    CC_LAUNCH_CHECK(dev);
+    return CC_OK;
+}

@@ -70,7 +70,8 @@ typedef struct cc_view {
 typedef struct cc_device_options {
     int32_t device_ordinal;        /* CUDA device index */
     int32_t debug_named_tensors;   /* with_name() snapshots tensors to host (cpu_tensor.rs:232-241) */
-    int32_t lazy;                  /* 0 = eager: one launch per trait call; 1 = record + fuse + CUDA-graph replay */
+    int32_t lazy;                  /* 0 = eager: one launch per trait call; 1 = record + fuse + CUDA-graph replay;
+                                      2 = as 1, and a fused token runs as ONE persistent kernel (mega.cu) */
     int32_t exact_order;           /* 1 = verification mode: every reduction in the reference's scalar order,
                                       bit-identical to the scalar CPU path (slow; see csrc/exact.cu) */
     uint64_t pool_bytes;           /* activation pool size hint, 0 = default */
