@@ -239,8 +239,7 @@ struct Fuser {
         const bool write_back = !dead_after(rn.a.buf, end);
         P.S(0x2001); P.SP(x); P.SP(og); P.SP(w); P.SP(act); P.S((uint64_t)n); uint32_t eb; memcpy(&eb, &eps, 4); P.S(eb); P.S(write_back);
         P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, og, w, eps, n, act, write_back); });
-        if (write_back) P.mega_ok = false;       // a grid-wide normq cannot update x in place (see fused.cu)
-        { MkPhase ph = {}; ph.type = MK_NORMQ; ph.x = x; ph.orig = og; ph.norm_w = w; ph.eps = eps; ph.n = (int)n; ph.act = cc_act_q8_0(act, n); P.phases.push_back(ph); }
+        { MkPhase ph = {}; ph.type = MK_NORMQ; ph.write_back = write_back; ph.x = x; ph.orig = og; ph.norm_w = w; ph.eps = eps; ph.n = (int)n; ph.act = cc_act_q8_0(act, n); P.phases.push_back(ph); }
         *xbuf = rn.a.buf;
         size_t used = (j + 2) - i;
         for (size_t t = i; t < i + used; t++) q[t].done = true;

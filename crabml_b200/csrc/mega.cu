@@ -52,6 +52,9 @@ __device__ void phase_normq(const MkPhase& ph, float* s_red) {
     const int n = ph.n;
     float* x = ph.x;
     float rms = 1.0f;
+    // write_back: the normalised row must be materialised in place -> one CTA does the whole row (nobody else may
+    // still be summing x while it is overwritten)
+    if (ph.write_back && blockIdx.x != 0) return;
     if (ph.norm_w) {
         float ss = 0.0f;
         const float4* x4 = (const float4*)x;
@@ -74,11 +77,11 @@ __device__ void phase_normq(const MkPhase& ph, float* s_red) {
     }
     ActQ8_0 act = ph.act;
     const int nb = n >> 5;
-    const int gw = blockIdx.x * MK_WARPS + warp, tw = gridDim.x * MK_WARPS;
+    const int gw = ph.write_back ? warp : blockIdx.x * MK_WARPS + warp, tw = ph.write_back ? MK_WARPS : gridDim.x * MK_WARPS;
     for (int b = gw; b < nb; b += tw) {
         float v = ldcg_f(x + b * 32 + lane);
         if (ph.orig) ph.orig[b * 32 + lane] = v;
-        if (ph.norm_w) v = (v / rms) * ph.norm_w[b * 32 + lane];
+        if (ph.norm_w) { v = (v / rms) * ph.norm_w[b * 32 + lane]; if (ph.write_back) x[b * 32 + lane] = v; }
         float amax = warp_max(fabsf(v));
         float d = amax / 127.0f;
         int q = __float2int_rz(v / d);
