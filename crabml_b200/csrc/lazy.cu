@@ -13,6 +13,7 @@
 // The activation pool hands out the same pointers for the same call sequence (LIFO free lists), which is what makes the
 // hash stable from token to token.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -46,6 +47,8 @@ struct LazyState {
     size_t dyn_cap = 1 << 16;
     void* act[2] = {nullptr, nullptr};
     unsigned* bar_dev = nullptr;     // megakernel grid barrier {count, generation}
+    unsigned long long* prof_dev = nullptr;   // CRABML_MEGA_PROF=1: per-phase start timestamps of the last megakernel run
+    std::vector<int> prof_types;
     size_t act_cap = 0;
     std::unordered_map<uint64_t, GraphEntry> cache;
     uint64_t flushes = 0, graph_hits = 0, captures = 0, uncached = 0;
@@ -73,6 +76,7 @@ LazyState* cc_lazy_create(cc_device* dev) {
     for (int i = 0; i < 2; i++)
         if (cudaMallocHost(&lz->dyn_host[i], lz->dyn_cap) != cudaSuccess || cudaEventCreateWithFlags(&lz->dyn_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete lz; return nullptr; }
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
+    if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 4096);
     if (cudaMalloc(&lz->bar_dev, 64) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 64) != cudaSuccess) { delete lz; return nullptr; }
     return lz;
 }
@@ -474,7 +478,9 @@ int cc_lazy_flush(cc_device* dev) {
             cudaError_t e = rc ? cudaSuccess : cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
             if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
             if (!rc) {
-                rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem) : run_steps(lz->dyn_dev);
+                if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue : 0)); }
+                rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem,
+                                               P.phases.size() < 4000 ? lz->prof_dev : nullptr) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);
                 if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: end capture: %s", cudaGetErrorString(e));
             }
@@ -510,6 +516,18 @@ int cc_lazy_flush(cc_device* dev) {
         if (op.a.buf) cc_tensor_release(op.a.buf);
     }
     return rc;
+}
+
+// developer profiling: per-phase start timestamps (ns) of the last megakernel run + phase type codes
+extern "C" CC_API int cc_lazy_mega_profile(cc_device* dev, unsigned long long* ts, int* types, int cap, int* n_out) {
+    if (!dev || !dev->lz || !dev->lz->prof_dev || !ts || !types || !n_out) return CC_ERR_ARG;
+    cudaStreamSynchronize(dev->stream);
+    int n = (int)dev->lz->prof_types.size();
+    if (n + 1 > cap) return CC_ERR_ARG;
+    if (cudaMemcpy(ts, dev->lz->prof_dev, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return CC_ERR_CUDA;
+    for (int i = 0; i < n; i++) types[i] = dev->lz->prof_types[i];
+    *n_out = n;
+    return CC_OK;
 }
 
 extern "C" CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out4) {

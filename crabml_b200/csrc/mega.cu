@@ -368,12 +368,19 @@ __device__ void phase_rows(const MkPhase& ph, const uint8_t* dyn) {
     }
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
-                                                                         unsigned* bar, const uint16_t* exp_lut) {
+                                                                         unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float s_red[MK_WARPS];
     __shared__ MkPhase s_ph;
     for (int p = 0; p < n_phases; p++) {
+        if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[p] = globaltimer_ns();     // phase start (developer profiling)
         // one copy of the descriptor per CTA
         {
             const int* src = (const int*)(phases + p);
@@ -393,6 +400,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         }
         if (p + 1 < n_phases) grid_barrier(bar, gridDim.x);
     }
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases] = globaltimer_ns();
 }
 
 size_t cc_mega_smem_for_matvec(int type, int k) {
@@ -400,14 +408,14 @@ size_t cc_mega_smem_for_matvec(int type, int k) {
     return nbp * 32 + nbp * 4 + (type == CC_Q4_0 ? nbp * 4 : 0);
 }
 
-int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem) {
+int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof) {
     int max_ctas_per_sm = 0;
     if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, mega_kernel, MK_THREADS, smem));
     CC_REQUIRE(dev, max_ctas_per_sm >= 1, "megakernel does not fit on an SM");
     int per_sm = max_ctas_per_sm < MK_CTAS_PER_SM ? max_ctas_per_sm : MK_CTAS_PER_SM;
     int grid = dev->sm_count * per_sm;          // all CTAs co-resident: required by the grid barrier
-    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut);
+    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut, prof);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }

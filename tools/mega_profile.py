@@ -1,0 +1,37 @@
+"""Per-phase time inside the megakernel (CRABML_MEGA_PROF=1): which phases/barriers the token time goes to."""
+import collections
+import ctypes as C
+import os
+import sys
+
+os.environ["CRABML_MEGA_PROF"] = "1"
+sys.path.insert(0, ".")
+import numpy as np  # noqa: E402
+from crabml_b200 import CudaTensorDevice, capi  # noqa: E402
+from crabml_b200 import runner as R  # noqa: E402
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "Q8_0"
+wt = {"Q8_0": capi.Q8_0, "Q4_0": capi.Q4_0}[wl]
+dev = CudaTensorDevice(0, lazy=2)
+conf = R.LLAMA2_7B
+w = R.synthetic_weights(dev, conf, wt, wt)
+r = R.LlamaRunner(dev, conf, w, 128)
+pos = 0
+for i in range(40):
+    r.forward([1 + i], pos, export=False); pos += 1
+dev.synchronize()
+ts = (C.c_uint64 * 4096)(); ty = (C.c_int32 * 4096)(); n = C.c_int32(0)
+dev.check(dev.lib.cc_lazy_mega_profile(dev.handle, ts, ty, 4096, C.byref(n)))
+n = n.value
+t = np.array(ts[:n + 1], dtype=np.float64)
+d = np.diff(t) / 1e3
+names = {0: "normq", 16 + 3: "qkv matvec(3)", 16 + 1 + 4: "matvec+residual", 16 + 2 + 8: "gate/up silu*mul", 16 + 1: "matvec(1)", 32: "attn", 48: "rows"}
+agg = collections.defaultdict(list)
+for i in range(n):
+    agg[names.get(ty[i], str(ty[i]))].append(d[i])
+print(f"phases {n}, token total {(t[-1] - t[0]) / 1e3:.1f} us (phase time includes the barrier that ends it)")
+for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    print(f"  {k:20s} n={len(v):3d}  sum {sum(v):8.1f} us  avg {np.mean(v):6.2f}  min {min(v):6.2f}  max {max(v):6.2f}")
+# the first layers in order
+print("first 10 phases:", [(names.get(ty[i], ty[i]), round(d[i], 2)) for i in range(min(10, n))])
+dev.close()
