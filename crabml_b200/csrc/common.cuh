@@ -211,7 +211,7 @@ struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; int64_t cols; };
 // megakernel phase descriptor (mega.cu); built by lazy.cu
 enum { MK_NORMQ = 0, MK_MATVEC = 1, MK_ATTN = 2, MK_ROWS = 3 };
 struct MkPhase {
-    int type, wtype, write_back, pad0;
+    int type, wtype, write_back, next_matvec;   // next_matvec: index of the next MATVEC phase (look-ahead prefetch), -1 if none
     // NORMQ (and the output quantisation of ATTN)
     float* x; float* orig; const float* norm_w; float eps; int n; ActQ8_0 act;
     StreamArgs mv;                      // MATVEC

@@ -471,6 +471,8 @@ int cc_lazy_flush(cc_device* dev) {
             GraphEntry ge;
             const bool use_mega = dev->mega && P.mega_ok && !P.phases.empty();
             if (use_mega) {       // phase table lives in device memory for the lifetime of the graph
+                int nxt = -1;
+                for (int t = (int)P.phases.size() - 1; t >= 0; t--) { P.phases[t].next_matvec = nxt; if (P.phases[t].type == MK_MATVEC) nxt = t; }
                 if (cudaMalloc(&ge.phases_dev, P.phases.size() * sizeof(MkPhase)) != cudaSuccess ||
                     cudaMemcpy(ge.phases_dev, P.phases.data(), P.phases.size() * sizeof(MkPhase), cudaMemcpyHostToDevice) != cudaSuccess)
                     rc = cc_fail(dev, CC_ERR_CUDA, "lazy: phase table upload failed");

@@ -95,13 +95,11 @@ __device__ void phase_normq(const MkPhase& ph, float* s_red) {
 __device__ __forceinline__ int mk_dp16(const int4& w, const int4& a) {
     return __dp4a(w.x, a.x, __dp4a(w.y, a.y, __dp4a(w.z, a.z, __dp4a(w.w, a.w, 0))));
 }
-template <int TYPE> struct MkSeg;
-template <> struct MkSeg<CC_Q8_0> { int4 a[MK_SEG], b[MK_SEG]; uint16_t s[MK_SEG]; };
-template <> struct MkSeg<CC_Q4_0> { int4 a[MK_SEG]; uint16_t s[MK_SEG]; };
+struct MkSeg { int4 a[MK_SEG], b[MK_SEG]; uint16_t s[MK_SEG]; };      // Q4_0 leaves b unused
 struct MkRowPtr { const uint8_t* q; const uint16_t* d; };
 
 template <int TYPE>
-__device__ __forceinline__ void mk_seg_load(MkSeg<TYPE>& S, const MkRowPtr& p, int seg, int nb, int GR, int last_half_off, int lane, bool valid) {
+__device__ __forceinline__ void mk_seg_load(MkSeg& S, const MkRowPtr& p, int seg, int nb, int GR, int last_half_off, int lane, bool valid) {
     constexpr int GB = TYPE == CC_Q8_0 ? 1024 : 512;
     const uint8_t* q = p.q + (size_t)seg * (MK_SEG * GB);
     const uint16_t* d = p.d + seg * (MK_SEG * 32);
@@ -120,7 +118,7 @@ __device__ __forceinline__ void mk_seg_load(MkSeg<TYPE>& S, const MkRowPtr& p, i
     }
 }
 template <int TYPE>
-__device__ __forceinline__ float mk_seg_dot(const MkSeg<TYPE>& S, int seg, const int4* aq_l, const float* ad_l, const int* as_l) {
+__device__ __forceinline__ float mk_seg_dot(const MkSeg& S, int seg, const int4* aq_l, const float* ad_l, const int* as_l) {
     float acc = 0.0f;
     const int4* aq = aq_l + seg * (MK_SEG * 64);
     const float* ad = ad_l + seg * (MK_SEG * 32);
@@ -140,44 +138,72 @@ __device__ __forceinline__ float mk_seg_dot(const MkSeg<TYPE>& S, int seg, const
     return acc;
 }
 
+// geometry of one MATVEC phase for this warp
+struct MkGeo {
+    int nb, GR, NSEG, U, last_half_off, gw, TW;
+    bool pair;
+};
+__device__ __forceinline__ MkGeo mk_geo(const StreamArgs& A) {
+    MkGeo g;
+    const int warp = threadIdx.x >> 5;
+    g.nb = A.k >> 5; g.GR = (g.nb + 31) >> 5; g.NSEG = (g.GR + MK_SEG - 1) / MK_SEG;
+    g.gw = blockIdx.x * MK_WARPS + warp; g.TW = gridDim.x * MK_WARPS;
+    g.pair = A.epilogue == 2;
+    const StreamMats& M = A.mats;
+    const int m_cat = g.pair ? M.m[0] : M.m[0] + (M.n > 1 ? M.m[1] : 0) + (M.n > 2 ? M.m[2] : 0);
+    const int n_rows = g.gw < m_cat ? (m_cat - g.gw + g.TW - 1) / g.TW : 0;
+    g.U = (g.pair ? 2 * n_rows : n_rows) * g.NSEG;
+    g.last_half_off = 16 * (g.nb - 32 * (g.GR - 1));
+    return g;
+}
 template <int TYPE>
-__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut) {
+__device__ __forceinline__ MkRowPtr mk_vrow_ptr(const StreamMats& M, const MkGeo& g, int i, int lane) {
+    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
+    int mat = 0, r;
+    if (g.pair) { mat = i & 1; r = g.gw + (i >> 1) * g.TW; }
+    else {
+        r = g.gw + i * g.TW;
+        if (M.n > 1 && r >= M.m[0]) { r -= M.m[0]; mat = 1; if (M.n > 2 && r >= M.m[1]) { r -= M.m[1]; mat = 2; } }
+    }
+    const uint8_t* q0 = mat == 0 ? M.qs[0] : mat == 1 ? M.qs[1] : M.qs[2];
+    const uint16_t* d0 = mat == 0 ? M.d[0] : mat == 1 ? M.d[1] : M.d[2];
+    MkRowPtr p;
+    p.q = q0 + (size_t)r * g.nb * BB + lane * 16;
+    p.d = d0 + (size_t)r * g.nb + lane;
+    return p;
+}
+
+// Issue the loads of this warp's first two segments of a MATVEC phase.  Weights are immutable, so this may run
+// long before the phase itself -- across barriers and small phases -- keeping HBM busy while the grid synchronises.
+template <int TYPE>
+__device__ __forceinline__ void matvec_prefetch(const StreamArgs& A, MkSeg& buf0, MkSeg& buf1) {
+    const int lane = threadIdx.x & 31;
+    const MkGeo g = mk_geo(A);
+    MkRowPtr p0 = mk_vrow_ptr<TYPE>(A.mats, g, 0, lane);
+    mk_seg_load<TYPE>(buf0, p0, 0, g.nb, g.GR, g.last_half_off, lane, g.U > 0);
+    if (g.NSEG > 1) mk_seg_load<TYPE>(buf1, p0, 1, g.nb, g.GR, g.last_half_off, lane, g.U > 1);
+    else { MkRowPtr p1 = mk_vrow_ptr<TYPE>(A.mats, g, 1, lane); mk_seg_load<TYPE>(buf1, p1, 0, g.nb, g.GR, g.last_half_off, lane, g.U > 1); }
+}
+
+// precondition: buf0 / buf1 hold this warp's segments 0 / 1 (matvec_prefetch)
+template <int TYPE>
+__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut, MkSeg& buf0, MkSeg& buf1) {
     const StreamArgs& A = ph.mv;
-    const int k = A.k, nb = k >> 5, GR = (nb + 31) >> 5, NSEG = (GR + MK_SEG - 1) / MK_SEG;
+    const int k = A.k;
+    const MkGeo g = mk_geo(A);
+    const int nb = g.nb, GR = g.GR, NSEG = g.NSEG, U = g.U, gw = g.gw, TW = g.TW;
+    const bool pair = g.pair;
     const int nbp = NSEG * MK_SEG * 32;
     int8_t* s_q = (int8_t*)smem;
     float* s_d = (float*)(smem + (size_t)nbp * 32);
     int* s_s = (int*)(smem + (size_t)nbp * 32 + (size_t)nbp * 4);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * MK_WARPS + warp, TW = gridDim.x * MK_WARPS;
+    const int lane = threadIdx.x & 31;
     const StreamMats& M = A.mats;
-    const bool pair = A.epilogue == 2;
-    const int m_cat = pair ? M.m[0] : M.m[0] + (M.n > 1 ? M.m[1] : 0) + (M.n > 2 ? M.m[2] : 0);
-    const int n_rows = gw < m_cat ? (m_cat - gw + TW - 1) / TW : 0;
-    const int n_vrows = pair ? 2 * n_rows : n_rows;
-    const int U = n_vrows * NSEG;
-    const int last_half_off = 16 * (nb - 32 * (GR - 1));
-    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
-
-    auto vrow_ptr = [&](int i) -> MkRowPtr {
-        int mat = 0, r;
-        if (pair) { mat = i & 1; r = gw + (i >> 1) * TW; }
-        else {
-            r = gw + i * TW;
-            if (M.n > 1 && r >= M.m[0]) { r -= M.m[0]; mat = 1; if (M.n > 2 && r >= M.m[1]) { r -= M.m[1]; mat = 2; } }
-        }
-        const uint8_t* q0 = mat == 0 ? M.qs[0] : mat == 1 ? M.qs[1] : M.qs[2];
-        const uint16_t* d0 = mat == 0 ? M.d[0] : mat == 1 ? M.d[1] : M.d[2];
-        MkRowPtr p;
-        p.q = q0 + (size_t)r * nb * BB + lane * 16;
-        p.d = d0 + (size_t)r * nb + lane;
-        return p;
-    };
-    MkSeg<TYPE> buf0, buf1;
+    // load cursor: points at segment 2
     int l_i = 0, l_seg = 0;
-    MkRowPtr l_ptr = vrow_ptr(0);
-    mk_seg_load<TYPE>(buf0, l_ptr, 0, nb, GR, last_half_off, lane, U > 0);
-    auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = vrow_ptr(++l_i); } };
+    MkRowPtr l_ptr = mk_vrow_ptr<TYPE>(M, g, 0, lane);
+    auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); } };
+    advance_load();
     advance_load();
     {   // stage the quantised activation (written by other CTAs in the previous phase: L2 loads)
         const uint8_t* act = (const uint8_t*)A.act;
@@ -206,9 +232,9 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         if (pair) {
             if ((i & 1) == 0) { first = r; return; }
             if (lane == 0) {
-                float g = first;
-                float nexp = h2f_bits(exp_lut[f2h_bits(-g)]);
-                M.out[0][gw + (i >> 1) * TW] = (g / (1.0f + nexp)) * r;
+                float gt = first;
+                float nexp = h2f_bits(exp_lut[f2h_bits(-gt)]);
+                M.out[0][gw + (i >> 1) * TW] = (gt / (1.0f + nexp)) * r;
             }
             return;
         }
@@ -220,16 +246,16 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
             o[rr] = r;
         }
     };
-    for (int u = 0; u < U; u += 2) {
-        mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, last_half_off, lane, u + 1 < U);
-        advance_load();
+    for (int u = 0; u < U; u += 2) {          // two segments (8 KB of Q8_0) in flight per warp at all times
         acc += mk_seg_dot<TYPE>(buf0, c_seg, aq_l, ad_l, as_l);
         finish_segment();
-        if (u + 1 >= U) break;
-        mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, last_half_off, lane, u + 2 < U);
+        mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 2 < U);
         advance_load();
+        if (u + 1 >= U) break;
         acc += mk_seg_dot<TYPE>(buf1, c_seg, aq_l, ad_l, as_l);
         finish_segment();
+        mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 3 < U);
+        advance_load();
     }
 }
 
@@ -273,24 +299,41 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
                 else { ((float*)a.kcache)[off] = s_k[i]; ((float*)a.vcache)[off] = s_v[i]; }
             }
         }
-        for (int s = warp; s < L; s += MK_WARPS) {
-            float acc = 0.0f;
-            if (s < kv_len) {
-                if (KV_F16) {
-                    const __half* kr = (const __half*)a.kcache + (int64_t)g * seq_stride + (int64_t)s * hd;
-                    for (int i = lane; i < hd; i += 32) acc += __half2float(__float2half_rn(s_q[i])) * __half2float(kr[i]);
-                } else {
-                    const float* kr = (const float*)a.kcache + (int64_t)g * seq_stride + (int64_t)s * hd;
-                    for (int i = lane; i < hd; i += 32) acc += s_q[i] * kr[i];
-                }
-            } else {
-                for (int i = lane; i < hd; i += 32) {
-                    if (KV_F16) acc += __half2float(__float2half_rn(s_q[i])) * __half2float(__float2half_rn(s_k[i]));
-                    else acc += s_q[i] * s_k[i];
+        // scores: PB positions per warp iteration, all their K loads issued before any is used (same per-lane summation
+        // order as fused.cu's attn_decode_kernel, so both modes give identical results)
+        constexpr int PB = 4, TMAX = 8;                  // hd <= 256
+        for (int s0 = warp; s0 < L; s0 += MK_WARPS * PB) {
+            float kv[PB][TMAX];
+#pragma unroll
+            for (int b = 0; b < PB; b++) {
+                const int s = s0 + b * MK_WARPS;
+#pragma unroll
+                for (int t = 0; t < TMAX; t++) {
+                    const int i = lane + 32 * t;
+                    float v = 0.0f;
+                    if (i < hd && s < L) {
+                        if (s < kv_len) {
+                            const int64_t off = (int64_t)g * seq_stride + (int64_t)s * hd + i;
+                            v = KV_F16 ? __half2float(((const __half*)a.kcache)[off]) : ((const float*)a.kcache)[off];
+                        } else {
+                            v = KV_F16 ? __half2float(__float2half_rn(s_k[i])) : s_k[i];
+                        }
+                    }
+                    kv[b][t] = v;
                 }
             }
-            acc = warp_sum(acc);
-            if (lane == 0) s_p[s] = acc;
+#pragma unroll
+            for (int b = 0; b < PB; b++) {
+                const int s = s0 + b * MK_WARPS;
+                float acc = 0.0f;
+#pragma unroll
+                for (int t = 0; t < TMAX; t++) {
+                    const int i = lane + 32 * t;
+                    if (i < hd) acc += (KV_F16 ? __half2float(__float2half_rn(s_q[i])) : s_q[i]) * kv[b][t];
+                }
+                acc = warp_sum(acc);
+                if (lane == 0 && s < L) s_p[s] = acc;
+            }
         }
         __syncthreads();
         float m = -INFINITY;
@@ -319,16 +362,29 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
         float* s_o = s_k;
         for (int d = threadIdx.x; d < hd; d += MK_THREADS) {
             float o;
+            // 8 V loads in flight, then the 8 accumulations in position order (the reference's order)
             if (KV_F16) {
                 const __half* vb = (const __half*)a.vcache + (int64_t)g * seq_stride + d;
                 __half acc = __float2half_rn(0.0f);
-                for (int s = 0; s < kv_len; s++) acc = __hadd(acc, __hmul(vb[(int64_t)s * hd], __float2half_rn(s_p[s])));
+                for (int s0 = 0; s0 < kv_len; s0 += 8) {
+                    __half v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = s0 + j < kv_len ? vb[(int64_t)(s0 + j) * hd] : __float2half_rn(0.0f);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (s0 + j < kv_len) acc = __hadd(acc, __hmul(v[j], __float2half_rn(s_p[s0 + j])));
+                }
                 acc = __hadd(acc, __hmul(__float2half_rn(s_v[d]), __float2half_rn(s_p[kv_len])));
                 o = __half2float(acc);
             } else {
                 const float* vb = (const float*)a.vcache + (int64_t)g * seq_stride + d;
                 float acc = 0.0f;
-                for (int s = 0; s < kv_len; s++) acc += s_p[s] * vb[(int64_t)s * hd];
+                for (int s0 = 0; s0 < kv_len; s0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = s0 + j < kv_len ? vb[(int64_t)(s0 + j) * hd] : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (s0 + j < kv_len) acc += s_p[s0 + j] * v[j];
+                }
                 acc += s_p[kv_len] * s_v[d];
                 o = acc;
             }
@@ -379,10 +435,13 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float s_red[MK_WARPS];
     __shared__ MkPhase s_ph;
+    __shared__ StreamArgs s_next;            // arguments of the next MATVEC phase (for the look-ahead prefetch)
+    __shared__ int s_next_type;
+    MkSeg buf0, buf1;                        // register-resident weight prefetch, live across phases and barriers
+    int prefetched = -1;                     // phase index whose first two segments sit in buf0 / buf1
     for (int p = 0; p < n_phases; p++) {
         if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[p] = globaltimer_ns();     // phase start (developer profiling)
-        // one copy of the descriptor per CTA
-        {
+        {   // one copy of the descriptor per CTA
             const int* src = (const int*)(phases + p);
             int* dst = (int*)&s_ph;
             for (int i = threadIdx.x; i < (int)(sizeof(MkPhase) / 4); i += MK_THREADS) dst[i] = src[i];
@@ -391,12 +450,33 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
-            if (s_ph.wtype == CC_Q8_0) phase_matvec<CC_Q8_0>(s_ph, smem, exp_lut); else phase_matvec<CC_Q4_0>(s_ph, smem, exp_lut);
+            if (s_ph.wtype == CC_Q8_0) {
+                if (prefetched != p) matvec_prefetch<CC_Q8_0>(s_ph.mv, buf0, buf1);
+                phase_matvec<CC_Q8_0>(s_ph, smem, exp_lut, buf0, buf1);
+            } else {
+                if (prefetched != p) matvec_prefetch<CC_Q4_0>(s_ph.mv, buf0, buf1);
+                phase_matvec<CC_Q4_0>(s_ph, smem, exp_lut, buf0, buf1);
+            }
             break;
         case MK_ATTN:
             if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)smem, s_red, dyn, exp_lut); else phase_attn<false>(s_ph, (float*)smem, s_red, dyn, exp_lut);
             break;
         case MK_ROWS: phase_rows(s_ph, dyn); break;
+        }
+        // look-ahead: request the first two weight segments of the next MATVEC phase before synchronising, so HBM keeps
+        // streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
+        const int nx = s_ph.next_matvec;
+        if (nx > p && nx < n_phases && prefetched != nx) {
+            __syncthreads();
+            {
+                const int* src = (const int*)&phases[nx].mv;
+                int* dst = (int*)&s_next;
+                for (int i = threadIdx.x; i < (int)(sizeof(StreamArgs) / 4); i += MK_THREADS) dst[i] = src[i];
+                if (threadIdx.x == 0) s_next_type = phases[nx].wtype;
+            }
+            __syncthreads();
+            if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, buf0, buf1); else matvec_prefetch<CC_Q4_0>(s_next, buf0, buf1);
+            prefetched = nx;
         }
         if (p + 1 < n_phases) grid_barrier(bar, gridDim.x);
     }
