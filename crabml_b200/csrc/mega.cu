@@ -10,6 +10,8 @@
 //     ROWS    copy_rows_from (embedding row dequantisation)
 // Data written by one CTA and read by another in a later phase is always read with ld.global.cg (L2), never through
 // the non-coherent L1.  All CTAs execute the same number of barriers.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dequant.cuh"
 
@@ -25,21 +27,29 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// sense-free generation barrier: bar[0] = arrival count, bar[1] = generation
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+// Split grid barrier: bar[0] = arrival count, bar[1] = generation.
+//   arrive : after the CTA's phase work (bar.sync), thread 0 publishes it (fence) and arrives;
+//   ...      the caller may now issue weight prefetch loads -- they must come AFTER the fence, otherwise the fence
+//            would sit on the critical path waiting for ~1 us HBM loads;
+//   wait   : thread 0 spins on the generation with ld.acquire (no fence: it would wait for the prefetch), then bar.sync.
+__device__ __forceinline__ unsigned grid_barrier_arrive(unsigned* bar, unsigned nblocks) {
     __syncthreads();
+    unsigned gen = 0;
     if (threadIdx.x == 0) {
-        const unsigned gen = ld_acquire_u32(&bar[1]);
+        gen = ld_acquire_u32(&bar[1]);
         __threadfence();
         const unsigned prev = atomicAdd(&bar[0], 1u);
         if (prev == nblocks - 1) {
             bar[0] = 0;
             __threadfence();
             st_release_u32(&bar[1], gen + 1);
-        } else {
-            while (ld_acquire_u32(&bar[1]) == gen) { }
         }
-        __threadfence();
+    }
+    return gen;
+}
+__device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned gen) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_u32(&bar[1]) == gen) { }
     }
     __syncthreads();
 }
@@ -431,7 +441,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
-                                                                         unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof) {
+                                                                         unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float s_red[MK_WARPS];
     __shared__ MkPhase s_ph;
@@ -466,8 +476,11 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         // look-ahead: request the first two weight segments of the next MATVEC phase before synchronising, so HBM keeps
         // streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
         const int nx = s_ph.next_matvec;
-        if (nx > p && nx < n_phases && prefetched != nx) {
-            __syncthreads();
+        const bool more = p + 1 < n_phases;
+        unsigned gen = 0;
+        if (more) gen = grid_barrier_arrive(bar, gridDim.x);
+        if ((flags & 1) && nx > p && nx < n_phases && prefetched != nx) {
+            if (!more) __syncthreads();
             {
                 const int* src = (const int*)&phases[nx].mv;
                 int* dst = (int*)&s_next;
@@ -478,7 +491,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, buf0, buf1); else matvec_prefetch<CC_Q4_0>(s_next, buf0, buf1);
             prefetched = nx;
         }
-        if (p + 1 < n_phases) grid_barrier(bar, gridDim.x);
+        if (more) grid_barrier_wait(bar, gen);
     }
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases] = globaltimer_ns();
 }
@@ -489,13 +502,14 @@ size_t cc_mega_smem_for_matvec(int type, int k) {
 }
 
 int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof) {
+    static const int flags = getenv("CRABML_MEGA_NOPREFETCH") ? 0 : 1;     // developer A/B switch
     int max_ctas_per_sm = 0;
     if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, mega_kernel, MK_THREADS, smem));
     CC_REQUIRE(dev, max_ctas_per_sm >= 1, "megakernel does not fit on an SM");
     int per_sm = max_ctas_per_sm < MK_CTAS_PER_SM ? max_ctas_per_sm : MK_CTAS_PER_SM;
     int grid = dev->sm_count * per_sm;          // all CTAs co-resident: required by the grid barrier
-    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut, prof);
+    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut, prof, flags);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }
