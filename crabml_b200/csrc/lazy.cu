@@ -77,7 +77,7 @@ LazyState* cc_lazy_create(cc_device* dev) {
         if (cudaMallocHost(&lz->dyn_host[i], lz->dyn_cap) != cudaSuccess || cudaEventCreateWithFlags(&lz->dyn_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete lz; return nullptr; }
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
     if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 4096);
-    if (cudaMalloc(&lz->bar_dev, 64) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 64) != cudaSuccess) { delete lz; return nullptr; }
+    if (cudaMalloc(&lz->bar_dev, 4096) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 4096) != cudaSuccess) { delete lz; return nullptr; }
     return lz;
 }
 void cc_lazy_destroy(cc_device* dev) {
@@ -359,7 +359,7 @@ struct Fuser {
             return cc_launch_attn_decode(d, B);
         });
         { MkPhase ph = {}; ph.type = MK_ATTN; ph.at = A; ph.dyn_off = dyn_off; ph.rope_off = roff; ph.act = cc_act_q8_0(lz->act[1], n_heads * hd);
-          P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, (size_t)(3 * hd + A.max_len + 8) * 4); }
+          P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, (size_t)(3 * hd + ((A.max_len + 8 + 3) & ~3) + 2 * 64 * hd) * 4 + 64); }
         *obuf = b2.out;
         for (size_t t = i; t < i + 9; t++) q[t].done = true;
         return 9;

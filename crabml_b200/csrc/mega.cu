@@ -32,24 +32,36 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm vo
 //   ...      the caller may now issue weight prefetch loads -- they must come AFTER the fence, otherwise the fence
 //            would sit on the critical path waiting for ~1 us HBM loads;
 //   wait   : thread 0 spins on the generation with ld.acquire (no fence: it would wait for the prefetch), then bar.sync.
+// Two-level arrival: same-address atomics serialise at L2 (~3 ns each, ~1 us for 296 CTAs), so CTAs first arrive on one
+// of MK_BAR_GROUPS counters (each on its own 128-byte line), and only the last CTA of a group arrives on the top counter.
+// Layout (u32 words): [0] top count, [32] generation, [64 + 32*g] group counters.
+#define MK_BAR_GROUPS 16
 __device__ __forceinline__ unsigned grid_barrier_arrive(unsigned* bar, unsigned nblocks) {
     __syncthreads();
     unsigned gen = 0;
     if (threadIdx.x == 0) {
-        gen = ld_acquire_u32(&bar[1]);
+        gen = ld_acquire_u32(&bar[32]);
         __threadfence();
-        const unsigned prev = atomicAdd(&bar[0], 1u);
-        if (prev == nblocks - 1) {
-            bar[0] = 0;
+        const unsigned g = blockIdx.x % MK_BAR_GROUPS;
+        const unsigned gsize = nblocks / MK_BAR_GROUPS + (g < nblocks % MK_BAR_GROUPS ? 1u : 0u);
+        const unsigned prev = atomicAdd(&bar[64 + 32 * g], 1u);
+        if (prev == gsize - 1) {
+            bar[64 + 32 * g] = 0;
             __threadfence();
-            st_release_u32(&bar[1], gen + 1);
+            const unsigned ngroups = nblocks < MK_BAR_GROUPS ? nblocks : MK_BAR_GROUPS;
+            const unsigned top = atomicAdd(&bar[0], 1u);
+            if (top == ngroups - 1) {
+                bar[0] = 0;
+                __threadfence();
+                st_release_u32(&bar[32], gen + 1);
+            }
         }
     }
     return gen;
 }
 __device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned gen) {
     if (threadIdx.x == 0) {
-        while (ld_acquire_u32(&bar[1]) == gen) { }
+        while (ld_acquire_u32(&bar[32]) == gen) { }
     }
     __syncthreads();
 }
@@ -65,6 +77,12 @@ __device__ void phase_normq(const MkPhase& ph, float* s_red) {
     // write_back: the normalised row must be materialised in place -> one CTA does the whole row (nobody else may
     // still be summing x while it is overwritten)
     if (ph.write_back && blockIdx.x != 0) return;
+    // this warp's blocks are requested first, so their latency overlaps the row pass below (one L2 round trip in total)
+    const int nb0 = n >> 5;
+    const int gw0 = ph.write_back ? warp : blockIdx.x * MK_WARPS + warp, tw0 = ph.write_back ? MK_WARPS : gridDim.x * MK_WARPS;
+    float pre[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const int b = gw0 + j * tw0; pre[j] = b < nb0 ? ldcg_f(x + b * 32 + lane) : 0.0f; }
     if (ph.norm_w) {
         float ss = 0.0f;
         const float4* x4 = (const float4*)x;
@@ -88,8 +106,7 @@ __device__ void phase_normq(const MkPhase& ph, float* s_red) {
     ActQ8_0 act = ph.act;
     const int nb = n >> 5;
     const int gw = ph.write_back ? warp : blockIdx.x * MK_WARPS + warp, tw = ph.write_back ? MK_WARPS : gridDim.x * MK_WARPS;
-    for (int b = gw; b < nb; b += tw) {
-        float v = ldcg_f(x + b * 32 + lane);
+    auto do_block = [&](int b, float v) {
         if (ph.orig) ph.orig[b * 32 + lane] = v;
         if (ph.norm_w) { v = (v / rms) * ph.norm_w[b * 32 + lane]; if (ph.write_back) x[b * 32 + lane] = v; }
         float amax = warp_max(fabsf(v));
@@ -98,7 +115,10 @@ __device__ void phase_normq(const MkPhase& ph, float* s_red) {
         act.qs[b * 32 + lane] = (int8_t)q;
         int s = warp_sum_i(q);
         if (lane == 0) { act.d[b] = __half2float(__float2half_rn(d)); act.isum[b] = s; }
-    }
+    };
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const int b = gw + j * tw; if (b < nb) do_block(b, pre[j]); }
+    for (int b = gw + 4 * tw; b < nb; b += tw) do_block(b, ldcg_f(x + b * 32 + lane));
 }
 
 // ---- MATVEC phase: the body of matvec_stream_kernel (see matvec_stream.cu for the design notes) -------------------------
@@ -269,7 +289,10 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
     }
 }
 
-// ---- ATTN phase: body of fused.cu attn_decode_kernel, heads dealt to CTAs ----------------------------------------------
+// ---- ATTN phase: arithmetic of fused.cu attn_decode_kernel, heads dealt to CTAs.  The K (then V) rows of the head are
+// staged in shared memory in chunks of AT_CH positions with ALL loads of a chunk in flight at once: at decode the cost of
+// this phase is HBM/L2 latency, not bandwidth, so round trips are what matters.
+#define AT_CH 64
 template <bool KV_F16>
 __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uint8_t* dyn, const uint16_t* exp_lut) {
     const AttnArgs& a = ph.at;
@@ -280,9 +303,27 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
     const int kv_len = (int)dynv[1], L = kv_len + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* s_q = sm; float* s_k = sm + hd; float* s_v = sm + 2 * hd; float* s_p = sm + 3 * hd;
+    float* s_kc = sm + 3 * hd + ((a.max_len + 8 + 3) & ~3);      // [AT_CH][hd] K chunk (as f32)
+    float* s_vc = s_kc + AT_CH * hd;                              // [AT_CH][hd] V chunk
     const int pairs = rope_dim >> 1;
+    const int hd4 = hd >> 2;
+    // stage `cnt` cache rows starting at position p0 of kv head g into dst (converted to f32); rows are contiguous
+    auto stage_rows = [&](const void* cache, int g, int p0, int cnt, float* dst) {
+        if (KV_F16) {
+            const __half2* src = (const __half2*)((const __half*)cache + (int64_t)g * seq_stride + (int64_t)p0 * hd);
+            for (int i = threadIdx.x; i < cnt * (hd >> 1); i += MK_THREADS) { float2 f = __half22float2(src[i]); dst[2 * i] = f.x; dst[2 * i + 1] = f.y; }
+        } else {
+            const float4* src = (const float4*)((const float*)cache + (int64_t)g * seq_stride + (int64_t)p0 * hd);
+            float4* d4 = (float4*)dst;
+            for (int i = threadIdx.x; i < cnt * hd4; i += MK_THREADS) d4[i] = src[i];
+        }
+    };
     for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
         const int g = KV_F16 ? h / (n_heads / n_kv) : h % n_kv;
+        // first K chunk (and, when the whole context fits one chunk, the V chunk too) are requested up front
+        const int c0 = min(kv_len, AT_CH);
+        stage_rows(a.kcache, g, 0, c0, s_kc);
+        if (kv_len <= AT_CH) stage_rows(a.vcache, g, 0, c0, s_vc);
         for (int i = threadIdx.x; i < hd; i += MK_THREADS) {
             float qv, kvv;
             if (i < rope_dim) {
@@ -309,41 +350,26 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
                 else { ((float*)a.kcache)[off] = s_k[i]; ((float*)a.vcache)[off] = s_v[i]; }
             }
         }
-        // scores: PB positions per warp iteration, all their K loads issued before any is used (same per-lane summation
-        // order as fused.cu's attn_decode_kernel, so both modes give identical results)
-        constexpr int PB = 4, TMAX = 8;                  // hd <= 256
-        for (int s0 = warp; s0 < L; s0 += MK_WARPS * PB) {
-            float kv[PB][TMAX];
-#pragma unroll
-            for (int b = 0; b < PB; b++) {
-                const int s = s0 + b * MK_WARPS;
-#pragma unroll
-                for (int t = 0; t < TMAX; t++) {
-                    const int i = lane + 32 * t;
-                    float v = 0.0f;
-                    if (i < hd && s < L) {
-                        if (s < kv_len) {
-                            const int64_t off = (int64_t)g * seq_stride + (int64_t)s * hd + i;
-                            v = KV_F16 ? __half2float(((const __half*)a.kcache)[off]) : ((const float*)a.kcache)[off];
-                        } else {
-                            v = KV_F16 ? __half2float(__float2half_rn(s_k[i])) : s_k[i];
-                        }
-                    }
-                    kv[b][t] = v;
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < PB; b++) {
-                const int s = s0 + b * MK_WARPS;
+        // scores, chunk by chunk; per-lane summation order i = lane, lane+32, ... as in fused.cu
+        for (int p0 = 0; p0 < kv_len; p0 += AT_CH) {
+            const int cnt = min(AT_CH, kv_len - p0);
+            if (p0 > 0) { __syncthreads(); stage_rows(a.kcache, g, p0, cnt, s_kc); __syncthreads(); }
+            for (int s = warp; s < cnt; s += MK_WARPS) {
+                const float* kr = s_kc + s * hd;
                 float acc = 0.0f;
-#pragma unroll
-                for (int t = 0; t < TMAX; t++) {
-                    const int i = lane + 32 * t;
-                    if (i < hd) acc += (KV_F16 ? __half2float(__float2half_rn(s_q[i])) : s_q[i]) * kv[b][t];
-                }
+                for (int i = lane; i < hd; i += 32) acc += (KV_F16 ? __half2float(__float2half_rn(s_q[i])) : s_q[i]) * kr[i];
                 acc = warp_sum(acc);
-                if (lane == 0 && s < L) s_p[s] = acc;
+                if (lane == 0) s_p[p0 + s] = acc;
             }
+        }
+        if (warp == 0) {                                           // this token's own position
+            float acc = 0.0f;
+            for (int i = lane; i < hd; i += 32) {
+                if (KV_F16) acc += __half2float(__float2half_rn(s_q[i])) * __half2float(__float2half_rn(s_k[i]));
+                else acc += s_q[i] * s_k[i];
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) s_p[kv_len] = acc;
         }
         __syncthreads();
         float m = -INFINITY;
@@ -369,35 +395,26 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
         for (int w = 0; w < MK_WARPS; w++) sum += s_red[w];
         for (int s = threadIdx.x; s < L; s += MK_THREADS) s_p[s] = s_p[s] / sum;
         __syncthreads();
-        float* s_o = s_k;
-        for (int d = threadIdx.x; d < hd; d += MK_THREADS) {
-            float o;
-            // 8 V loads in flight, then the 8 accumulations in position order (the reference's order)
-            if (KV_F16) {
-                const __half* vb = (const __half*)a.vcache + (int64_t)g * seq_stride + d;
-                __half acc = __float2half_rn(0.0f);
-                for (int s0 = 0; s0 < kv_len; s0 += 8) {
-                    __half v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = s0 + j < kv_len ? vb[(int64_t)(s0 + j) * hd] : __float2half_rn(0.0f);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) if (s0 + j < kv_len) acc = __hadd(acc, __hmul(v[j], __float2half_rn(s_p[s0 + j])));
+        // out[d] = sum_s p[s] * V[s][d], sequential over s (batch_matmul.rs:60-68 order); F16: f16 accumulation (buf_f16.rs:152-163)
+        float accf = 0.0f;
+        __half acch = __float2half_rn(0.0f);
+        const int d = threadIdx.x;
+        for (int p0 = 0; p0 < kv_len; p0 += AT_CH) {
+            const int cnt = min(AT_CH, kv_len - p0);
+            if (kv_len > AT_CH) { __syncthreads(); stage_rows(a.vcache, g, p0, cnt, s_vc); __syncthreads(); }
+            if (d < hd) {
+                for (int s = 0; s < cnt; s++) {
+                    if (KV_F16) acch = __hadd(acch, __hmul(__float2half_rn(s_vc[s * hd + d]), __float2half_rn(s_p[p0 + s])));
+                    else accf += s_p[p0 + s] * s_vc[s * hd + d];
                 }
-                acc = __hadd(acc, __hmul(__float2half_rn(s_v[d]), __float2half_rn(s_p[kv_len])));
-                o = __half2float(acc);
-            } else {
-                const float* vb = (const float*)a.vcache + (int64_t)g * seq_stride + d;
-                float acc = 0.0f;
-                for (int s0 = 0; s0 < kv_len; s0 += 8) {
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = s0 + j < kv_len ? vb[(int64_t)(s0 + j) * hd] : 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) if (s0 + j < kv_len) acc += s_p[s0 + j] * v[j];
-                }
-                acc += s_p[kv_len] * s_v[d];
-                o = acc;
             }
+        }
+        float* s_o = s_k;
+        __syncthreads();
+        if (d < hd) {
+            float o;
+            if (KV_F16) { acch = __hadd(acch, __hmul(__float2half_rn(s_v[d]), __float2half_rn(s_p[kv_len]))); o = __half2float(acch); }
+            else { accf += s_p[kv_len] * s_v[d]; o = accf; }
             a.out[h * hd + d] = o;
             s_o[d] = o;
         }
@@ -407,12 +424,12 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
             for (int b = warp; b < (hd >> 5); b += MK_WARPS) {
                 float v = s_o[b * 32 + lane];
                 float amax = warp_max(fabsf(v));
-                float d = amax / 127.0f;
-                int qq = __float2int_rz(v / d);
+                float dd = amax / 127.0f;
+                int qq = __float2int_rz(v / dd);
                 const int gb = h * (hd >> 5) + b;
                 act.qs[gb * 32 + lane] = (int8_t)qq;
                 int ss = warp_sum_i(qq);
-                if (lane == 0) { act.d[gb] = __half2float(__float2half_rn(d)); act.isum[gb] = ss; }
+                if (lane == 0) { act.d[gb] = __half2float(__float2half_rn(dd)); act.isum[gb] = ss; }
             }
         }
         __syncthreads();
