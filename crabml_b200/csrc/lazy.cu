@@ -481,6 +481,7 @@ int cc_lazy_flush(cc_device* dev) {
             if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
             if (!rc) {
                 if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue : 0)); }
+                if (use_mega) cudaMemsetAsync(lz->bar_dev, 0, 4096, dev->stream);      // (captured) barrier counters restart from 0 in every replay
                 rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem,
                                                P.phases.size() < 4000 ? lz->prof_dev : nullptr) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);

@@ -27,41 +27,34 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// Split grid barrier: bar[0] = arrival count, bar[1] = generation.
-//   arrive : after the CTA's phase work (bar.sync), thread 0 publishes it (fence) and arrives;
-//   ...      the caller may now issue weight prefetch loads -- they must come AFTER the fence, otherwise the fence
-//            would sit on the critical path waiting for ~1 us HBM loads;
-//   wait   : thread 0 spins on the generation with ld.acquire (no fence: it would wait for the prefetch), then bar.sync.
-// Two-level arrival: same-address atomics serialise at L2 (~3 ns each, ~1 us for 296 CTAs), so CTAs first arrive on one
-// of MK_BAR_GROUPS counters (each on its own 128-byte line), and only the last CTA of a group arrives on the top counter.
-// Layout (u32 words): [0] top count, [32] generation, [64 + 32*g] group counters.
+// Split grid barrier with monotonic counters (no resets, no separate fences: release/acquire ride on the atomics).
+// Layout (u32 words, each on its own 128-byte line): [0] top counter, [32] generation, [64 + 32*g] group counters.
+// Same-address atomics serialise at L2 (~3 ns each), so CTAs first arrive on one of MK_BAR_GROUPS group counters and only
+// the last CTA of a group arrives on the top counter.  `gen` is the number of barriers completed so far (tracked in a
+// register by thread 0; all CTAs execute the same barriers), so after barrier #gen every counter equals gen * its fan-in.
+//   arrive : bar.sync, then thread 0 arrives (atom.add.acq_rel = publishes the CTA's phase output);
+//   ...      the caller may now issue weight prefetch loads (AFTER the release, so nothing waits for them);
+//   wait   : thread 0 spins on the generation word with ld.acquire, then bar.sync.
 #define MK_BAR_GROUPS 16
-__device__ __forceinline__ unsigned grid_barrier_arrive(unsigned* bar, unsigned nblocks) {
+__device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen) {
     __syncthreads();
-    unsigned gen = 0;
     if (threadIdx.x == 0) {
-        gen = ld_acquire_u32(&bar[32]);
-        __threadfence();
         const unsigned g = blockIdx.x % MK_BAR_GROUPS;
         const unsigned gsize = nblocks / MK_BAR_GROUPS + (g < nblocks % MK_BAR_GROUPS ? 1u : 0u);
-        const unsigned prev = atomicAdd(&bar[64 + 32 * g], 1u);
-        if (prev == gsize - 1) {
-            bar[64 + 32 * g] = 0;
-            __threadfence();
-            const unsigned ngroups = nblocks < MK_BAR_GROUPS ? nblocks : MK_BAR_GROUPS;
-            const unsigned top = atomicAdd(&bar[0], 1u);
-            if (top == ngroups - 1) {
-                bar[0] = 0;
-                __threadfence();
-                st_release_u32(&bar[32], gen + 1);
-            }
+        const unsigned ngroups = nblocks < MK_BAR_GROUPS ? nblocks : MK_BAR_GROUPS;
+        if (atom_add_acq_rel(&bar[64 + 32 * g], 1u) + 1u == (gen + 1u) * gsize) {
+            if (atom_add_acq_rel(&bar[0], 1u) + 1u == (gen + 1u) * ngroups) st_release_u32(&bar[32], gen + 1u);
         }
     }
-    return gen;
 }
 __device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned gen) {
     if (threadIdx.x == 0) {
-        while (ld_acquire_u32(&bar[32]) == gen) { }
+        while (ld_acquire_u32(&bar[32]) != gen + 1u) { }
     }
     __syncthreads();
 }
@@ -461,19 +454,24 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
                                                                          unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float s_red[MK_WARPS];
-    __shared__ MkPhase s_ph;
+    __shared__ MkPhase s_phs[2];             // phase descriptors, double-buffered: p+1 is fetched while p runs
     __shared__ StreamArgs s_next;            // arguments of the next MATVEC phase (for the look-ahead prefetch)
     __shared__ int s_next_type;
     MkSeg buf0, buf1;                        // register-resident weight prefetch, live across phases and barriers
     int prefetched = -1;                     // phase index whose first two segments sit in buf0 / buf1
+    unsigned gen = 0;                        // barriers completed (thread 0 only); starts from the value left by the last launch
+    if (threadIdx.x == 0) gen = ld_acquire_u32(&bar[32]);
+    auto fetch_desc = [&](int p) {
+        const int* src = (const int*)(phases + p);
+        int* dst = (int*)&s_phs[p & 1];
+        for (int i = threadIdx.x; i < (int)(sizeof(MkPhase) / 4); i += MK_THREADS) dst[i] = src[i];
+    };
+    fetch_desc(0);
     for (int p = 0; p < n_phases; p++) {
         if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[p] = globaltimer_ns();     // phase start (developer profiling)
-        {   // one copy of the descriptor per CTA
-            const int* src = (const int*)(phases + p);
-            int* dst = (int*)&s_ph;
-            for (int i = threadIdx.x; i < (int)(sizeof(MkPhase) / 4); i += MK_THREADS) dst[i] = src[i];
-        }
-        __syncthreads();
+        __syncthreads();                     // descriptor p is in shared memory (fetched one phase ago)
+        if (p + 1 < n_phases) fetch_desc(p + 1);
+        const MkPhase& s_ph = s_phs[p & 1];
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
@@ -490,12 +488,11 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             break;
         case MK_ROWS: phase_rows(s_ph, dyn); break;
         }
-        // look-ahead: request the first two weight segments of the next MATVEC phase before synchronising, so HBM keeps
-        // streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
+        // look-ahead: request the first two weight segments of the next MATVEC phase before waiting at the barrier, so HBM
+        // keeps streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
         const int nx = s_ph.next_matvec;
         const bool more = p + 1 < n_phases;
-        unsigned gen = 0;
-        if (more) gen = grid_barrier_arrive(bar, gridDim.x);
+        if (more) grid_barrier_arrive(bar, gridDim.x, gen);
         if ((flags & 1) && nx > p && nx < n_phases && prefetched != nx) {
             if (!more) __syncthreads();
             {
@@ -508,7 +505,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, buf0, buf1); else matvec_prefetch<CC_Q4_0>(s_next, buf0, buf1);
             prefetched = nx;
         }
-        if (more) grid_barrier_wait(bar, gen);
+        if (more) { grid_barrier_wait(bar, gen); gen++; }
     }
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases] = globaltimer_ns();
 }
