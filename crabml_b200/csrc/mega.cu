@@ -11,6 +11,7 @@
 // Data written by one CTA and read by another in a later phase is always read with ld.global.cg (L2), never through
 // the non-coherent L1.  All CTAs execute the same number of barriers.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "dequant.cuh"
@@ -513,6 +514,33 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
 size_t cc_mega_smem_for_matvec(int type, int k) {
     size_t nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
     return nbp * 32 + nbp * 4 + (type == CC_Q4_0 ? nbp * 4 : 0);
+}
+
+// developer hook: a table of `n` empty phases -> the pure per-phase floor (descriptor fetch + grid barrier)
+extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase) {
+    if (!dev || n < 2 || !us_per_phase) return CC_ERR_ARG;
+    std::vector<MkPhase> tab((size_t)n);
+    for (auto& p : tab) { memset(&p, 0, sizeof(p)); p.type = 99; p.next_matvec = -1; }
+    MkPhase* d_tab = nullptr; unsigned* d_bar = nullptr;
+    CC_CUDA(dev, cudaMalloc(&d_tab, tab.size() * sizeof(MkPhase)));
+    CC_CUDA(dev, cudaMalloc(&d_bar, 4096));
+    CC_CUDA(dev, cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(MkPhase), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CC_CUDA(dev, cudaMemsetAsync(d_bar, 0, 4096, dev->stream));
+        cudaEventRecord(e0, dev->stream);
+        int rc = cc_launch_mega(dev, d_tab, n, nullptr, d_bar, 1024, nullptr);
+        if (rc) return rc;
+        cudaEventRecord(e1, dev->stream);
+        CC_CUDA(dev, cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    *us_per_phase = best * 1e3f / (float)n;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_tab); cudaFree(d_bar);
+    return CC_OK;
 }
 
 int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof) {

@@ -88,6 +88,8 @@ CC_API int cc_device_flush(cc_device* dev);
 /* lazy mode statistics, 8 values: {flushes, graph replays, graph captures, uncached (eager) flushes,
  * host ns spent recording, fusing, submitting, ops recorded} */
 CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out8);
+/* developer hook: per-phase floor of the megakernel (descriptor fetch + grid barrier), microseconds */
+CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase);
 /* developer profiling (CRABML_MEGA_PROF=1): phase start timestamps of the last megakernel run */
 CC_API int cc_lazy_mega_profile(cc_device* dev, unsigned long long* ts, int* types, int cap, int* n_out);
 /* counters: kernels launched by this library since creation (bench.py "gpu_launches") */
