@@ -16,9 +16,10 @@
 #include "common.cuh"
 #include "dequant.cuh"
 
-#define MK_THREADS 256
-#define MK_WARPS 8
-#define MK_CTAS_PER_SM 2
+// one CTA of 16 warps per SM: the grid barrier has 148 participants instead of 296 (its cost is what bounds a phase)
+#define MK_THREADS 512
+#define MK_WARPS 16
+#define MK_CTAS_PER_SM 1
 #define MK_SEG 4
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
