@@ -43,6 +43,31 @@ __device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* p, unsigned v) {
     asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
     return old;
 }
+__device__ __forceinline__ void red_add_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// variant 1/2: flat counter, fire-and-forget arrivals (red.release); CTA 0 watches the counter and publishes the generation
+__device__ __forceinline__ void grid_barrier_arrive_v1(unsigned* bar, unsigned nblocks, unsigned gen) {
+    __syncthreads();
+    if (threadIdx.x == MK_THREADS - 1) red_add_release(&bar[0], 1u);
+}
+__device__ __forceinline__ void grid_barrier_wait_v1(unsigned* bar, unsigned nblocks, unsigned gen, bool relaxed_poll) {
+    if (threadIdx.x == MK_THREADS - 1) {
+        if (blockIdx.x == 0) {
+            const unsigned target = (gen + 1u) * nblocks;
+            if (relaxed_poll) { while (ld_relaxed_u32(&bar[0]) != target) { } __threadfence(); }
+            else { while (ld_acquire_u32(&bar[0]) != target) { } }
+            st_release_u32(&bar[32], gen + 1u);
+        } else {
+            if (relaxed_poll) { while (ld_relaxed_u32(&bar[32]) != gen + 1u) { } __threadfence(); }
+            else { while (ld_acquire_u32(&bar[32]) != gen + 1u) { } }
+        }
+    }
+    __syncthreads();
+}
 __device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -461,8 +486,9 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     __shared__ int s_next_type;
     MkSeg buf0, buf1;                        // register-resident weight prefetch, live across phases and barriers
     int prefetched = -1;                     // phase index whose first two segments sit in buf0 / buf1
-    unsigned gen = 0;                        // barriers completed (thread 0 only); starts from the value left by the last launch
-    if (threadIdx.x == 0) gen = ld_acquire_u32(&bar[32]);
+    unsigned gen = 0;                        // barriers completed; starts from the value left by the last launch
+    const int bvar = (flags >> 4) & 3;       // barrier variant (developer experiment)
+    if (threadIdx.x == 0 || threadIdx.x == MK_THREADS - 1) gen = ld_acquire_u32(&bar[32]);
     auto fetch_desc = [&](int p) {
         const int* src = (const int*)(phases + p);
         int* dst = (int*)&s_phs[p & 1];
@@ -472,8 +498,8 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     for (int p = 0; p < n_phases; p++) {
         if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[p] = globaltimer_ns();     // phase start (developer profiling)
         __syncthreads();                     // descriptor p is in shared memory (fetched one phase ago)
-        if (p + 1 < n_phases) fetch_desc(p + 1);
-        const MkPhase& s_ph = s_phs[p & 1];
+        if (p + 1 < n_phases && !(flags & 8)) fetch_desc(p + 1);
+        const MkPhase& s_ph = s_phs[(flags & 8) ? 0 : (p & 1)];
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
@@ -494,7 +520,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         // keeps streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
         const int nx = s_ph.next_matvec;
         const bool more = p + 1 < n_phases;
-        if (more) grid_barrier_arrive(bar, gridDim.x, gen);
+        if (more) { if (bvar == 0) grid_barrier_arrive(bar, gridDim.x, gen); else grid_barrier_arrive_v1(bar, gridDim.x, gen); }
         if ((flags & 1) && nx > p && nx < n_phases && prefetched != nx) {
             if (!more) __syncthreads();
             {
@@ -507,7 +533,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, buf0, buf1); else matvec_prefetch<CC_Q4_0>(s_next, buf0, buf1);
             prefetched = nx;
         }
-        if (more) { grid_barrier_wait(bar, gen); gen++; }
+        if (more) { if (bvar == 0) grid_barrier_wait(bar, gen); else grid_barrier_wait_v1(bar, gridDim.x, gen, bvar == 2); gen++; }
     }
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases] = globaltimer_ns();
 }
@@ -545,7 +571,7 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
 }
 
 int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof) {
-    static const int flags = getenv("CRABML_MEGA_NOPREFETCH") ? 0 : 1;     // developer A/B switch
+    static const int flags = (getenv("CRABML_MEGA_NOPREFETCH") ? 0 : 1) | (getenv("CRABML_MEGA_FLAGS") ? atoi(getenv("CRABML_MEGA_FLAGS")) : 0);     // developer A/B switches
     int max_ctas_per_sm = 0;
     if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, mega_kernel, MK_THREADS, smem));
