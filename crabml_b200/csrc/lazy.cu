@@ -383,6 +383,17 @@ struct Fuser {
         return 1;
     }
 
+    // megakernel only: phases[at] = NORMQ (not write-back) directly followed by its single MATVEC consumer -> one MATVEC
+    // phase with a fused prologue (saves a grid barrier per merge; see mega.cu phase_matvec)
+    void merge_prologue(size_t at) {
+        if (at + 2 != P.phases.size()) return;
+        MkPhase& nq = P.phases[at];
+        MkPhase& mv = P.phases[at + 1];
+        if (nq.type != MK_NORMQ || mv.type != MK_MATVEC || nq.write_back || nq.n != mv.mv.k) return;
+        mv.x = nq.x; mv.orig = nq.orig; mv.norm_w = nq.norm_w; mv.eps = nq.eps; mv.n = nq.n;
+        P.phases.erase(P.phases.begin() + at);
+    }
+
     void run() {
         size_t i = 0;
         while (i < q.size()) {
@@ -393,7 +404,10 @@ struct Fuser {
             if ((used = try_normq(i, 0, &xb))) {
                 i += used;
                 // every following group of matvecs on the normalised x reuses scratch 0
-                while (size_t u2 = try_stream(i, xb, 0)) i += u2;
+                const size_t ph0 = P.phases.size();
+                int groups = 0;
+                while (size_t u2 = try_stream(i, xb, 0)) { i += u2; groups++; }
+                if (groups == 1) merge_prologue(ph0 - 1);
                 continue;
             }
             bool quantized = false;
@@ -403,7 +417,8 @@ struct Fuser {
                 continue;
             }
             if (is(i, L_MATVEC) && q[i].b.buf->dtype == CC_F32 && (q[i].b.ndim == 1 || q[i].b.shape[0] == 1)) {
-                if ((used = try_stream(i, q[i].b.buf, -1))) { i += used; continue; }
+                const size_t ph0 = P.phases.size();
+                if ((used = try_stream(i, q[i].b.buf, -1))) { i += used; merge_prologue(ph0); continue; }
             }
             fallback(i);
             i++;

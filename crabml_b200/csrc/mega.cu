@@ -29,59 +29,30 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// Split grid barrier with monotonic counters (no resets, no separate fences: release/acquire ride on the atomics).
-// Layout (u32 words, each on its own 128-byte line): [0] top counter, [32] generation, [64 + 32*g] group counters.
-// Same-address atomics serialise at L2 (~3 ns each), so CTAs first arrive on one of MK_BAR_GROUPS group counters and only
-// the last CTA of a group arrives on the top counter.  `gen` is the number of barriers completed so far (tracked in a
-// register by thread 0; all CTAs execute the same barriers), so after barrier #gen every counter equals gen * its fan-in.
-//   arrive : bar.sync, then thread 0 arrives (atom.add.acq_rel = publishes the CTA's phase output);
-//   ...      the caller may now issue weight prefetch loads (AFTER the release, so nothing waits for them);
-//   wait   : thread 0 spins on the generation word with ld.acquire, then bar.sync.
-#define MK_BAR_GROUPS 16
-__device__ __forceinline__ unsigned atom_add_acq_rel(unsigned* p, unsigned v) {
-    unsigned old;
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
-}
+// Split grid barrier (measured with tools/barrier_floor.py on B200, 148 CTAs: 2.1 us per phase; the two-level
+// acq_rel-atomic version cost 3.1 us, relaxed polling + fence 2.6 us):
+//   arrive : bar.sync, then ONE thread does a fire-and-forget red.release.gpu.add on a flat monotonic counter
+//            (the release publishes the CTA's phase output; that thread never issues prefetch loads);
+//   ...      the other warps may already issue the next phase's weight prefetch;
+//   wait   : CTA 0 watches the counter reach (gen+1) * nblocks and publishes the generation word; everyone else spins on
+//            the generation with ld.acquire; then bar.sync.
+// Layout (u32 words on separate 128-byte lines): [0] arrival counter, [32] generation.  Counters are zeroed by a memset node
+// at the head of every graph replay, so `gen` starts at 0.
 __device__ __forceinline__ void red_add_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// variant 1/2: flat counter, fire-and-forget arrivals (red.release); CTA 0 watches the counter and publishes the generation
-__device__ __forceinline__ void grid_barrier_arrive_v1(unsigned* bar, unsigned nblocks, unsigned gen) {
-    __syncthreads();
-    if (threadIdx.x == MK_THREADS - 1) red_add_release(&bar[0], 1u);
-}
-__device__ __forceinline__ void grid_barrier_wait_v1(unsigned* bar, unsigned nblocks, unsigned gen, bool relaxed_poll) {
-    if (threadIdx.x == MK_THREADS - 1) {
-        if (blockIdx.x == 0) {
-            const unsigned target = (gen + 1u) * nblocks;
-            if (relaxed_poll) { while (ld_relaxed_u32(&bar[0]) != target) { } __threadfence(); }
-            else { while (ld_acquire_u32(&bar[0]) != target) { } }
-            st_release_u32(&bar[32], gen + 1u);
-        } else {
-            if (relaxed_poll) { while (ld_relaxed_u32(&bar[32]) != gen + 1u) { } __threadfence(); }
-            else { while (ld_acquire_u32(&bar[32]) != gen + 1u) { } }
-        }
-    }
-    __syncthreads();
-}
+#define MK_BAR_THREAD (MK_THREADS - 1)
 __device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned g = blockIdx.x % MK_BAR_GROUPS;
-        const unsigned gsize = nblocks / MK_BAR_GROUPS + (g < nblocks % MK_BAR_GROUPS ? 1u : 0u);
-        const unsigned ngroups = nblocks < MK_BAR_GROUPS ? nblocks : MK_BAR_GROUPS;
-        if (atom_add_acq_rel(&bar[64 + 32 * g], 1u) + 1u == (gen + 1u) * gsize) {
-            if (atom_add_acq_rel(&bar[0], 1u) + 1u == (gen + 1u) * ngroups) st_release_u32(&bar[32], gen + 1u);
-        }
-    }
+    if (threadIdx.x == MK_BAR_THREAD) red_add_release(&bar[0], 1u);
 }
-__device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned gen) {
-    if (threadIdx.x == 0) {
-        while (ld_acquire_u32(&bar[32]) != gen + 1u) { }
+__device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblocks, unsigned gen) {
+    if (threadIdx.x == MK_BAR_THREAD) {
+        if (blockIdx.x == 0) {
+            const unsigned target = (gen + 1u) * nblocks;
+            while (ld_acquire_u32(&bar[0]) != target) { }
+            st_release_u32(&bar[32], gen + 1u);
+        } else {
+            while (ld_acquire_u32(&bar[32]) != gen + 1u) { }
+        }
     }
     __syncthreads();
 }
@@ -255,7 +226,55 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
     auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); } };
     advance_load();
     advance_load();
-    {   // stage the quantised activation (written by other CTAs in the previous phase: L2 loads)
+    if (ph.x) {
+        // Fused prologue: [rms_norm * w] + Q8_0 quantisation of x, computed by EVERY CTA straight into its shared memory
+        // (redundant across SMs, ~1.5 us of issue time) -- cheaper than a separate NORMQ phase, which costs a grid barrier
+        // (~2.1 us) plus its own latency chain.  The weight segments requested by matvec_prefetch are in flight meanwhile.
+        const float* x = ph.x;
+        const int n = k;
+        const int warp = threadIdx.x >> 5;
+        float rms = 1.0f;
+        if (ph.norm_w) {
+            float ss = 0.0f;
+            const float4* x4 = (const float4*)x;
+            const int n4 = n >> 2;
+            for (int i0 = 0; i0 < n4; i0 += MK_THREADS * 4) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { int i = i0 + j * MK_THREADS + threadIdx.x; v[j] = i < n4 ? __ldcg(x4 + i) : make_float4(0, 0, 0, 0); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+            }
+            ss = warp_sum(ss);
+            float* s_red = (float*)(smem + (size_t)nbp * 32 + (size_t)nbp * 8);     // scratch behind the activation arrays
+            if (lane == 0) s_red[warp] = ss;
+            __syncthreads();
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < MK_WARPS; w++) t += s_red[w];
+            rms = sqrtf(t / (float)n + ph.eps);
+        }
+        if (ph.orig && blockIdx.x == 0)                              // Tensor::dup of the un-normalised row (llama2.rs:227,607)
+            for (int i = threadIdx.x; i < n; i += MK_THREADS) ph.orig[i] = ldcg_f(x + i);
+        for (int b0 = 0; b0 < nbp; b0 += MK_WARPS * 4) {             // 4 blocks per warp per pass, loads first
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int b = b0 + j * MK_WARPS + warp; v[j] = b < nb ? ldcg_f(x + b * 32 + lane) : 0.0f; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int b = b0 + j * MK_WARPS + warp;
+                if (b >= nbp) continue;
+                float xv = v[j];
+                if (ph.norm_w && b < nb) xv = (xv / rms) * ph.norm_w[b * 32 + lane];
+                float amax = warp_max(fabsf(xv));
+                float d = amax / 127.0f;
+                int q = b < nb ? __float2int_rz(xv / d) : 0;
+                s_q[b * 32 + lane] = (int8_t)q;
+                if constexpr (TYPE == CC_Q4_0) { int sq = warp_sum_i(q); if (lane == 0) s_s[b] = sq; }
+                if (lane == 0) s_d[b] = b < nb ? __half2float(__float2half_rn(d)) : 0.0f;
+            }
+        }
+    } else {   // stage the quantised activation (written by other CTAs in the previous phase: L2 loads)
         const uint8_t* act = (const uint8_t*)A.act;
         const int4* gq = (const int4*)act;
         int4* sq4 = (int4*)s_q;
@@ -487,8 +506,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     MkSeg buf0, buf1;                        // register-resident weight prefetch, live across phases and barriers
     int prefetched = -1;                     // phase index whose first two segments sit in buf0 / buf1
     unsigned gen = 0;                        // barriers completed; starts from the value left by the last launch
-    const int bvar = (flags >> 4) & 3;       // barrier variant (developer experiment)
-    if (threadIdx.x == 0 || threadIdx.x == MK_THREADS - 1) gen = ld_acquire_u32(&bar[32]);
+    if (threadIdx.x == MK_BAR_THREAD) gen = ld_acquire_u32(&bar[32]);
     auto fetch_desc = [&](int p) {
         const int* src = (const int*)(phases + p);
         int* dst = (int*)&s_phs[p & 1];
@@ -498,8 +516,8 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     for (int p = 0; p < n_phases; p++) {
         if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[p] = globaltimer_ns();     // phase start (developer profiling)
         __syncthreads();                     // descriptor p is in shared memory (fetched one phase ago)
-        if (p + 1 < n_phases && !(flags & 8)) fetch_desc(p + 1);
-        const MkPhase& s_ph = s_phs[(flags & 8) ? 0 : (p & 1)];
+        if (p + 1 < n_phases) fetch_desc(p + 1);
+        const MkPhase& s_ph = s_phs[p & 1];
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
@@ -520,7 +538,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         // keeps streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
         const int nx = s_ph.next_matvec;
         const bool more = p + 1 < n_phases;
-        if (more) { if (bvar == 0) grid_barrier_arrive(bar, gridDim.x, gen); else grid_barrier_arrive_v1(bar, gridDim.x, gen); }
+        if (more) grid_barrier_arrive(bar, gridDim.x, gen);
         if ((flags & 1) && nx > p && nx < n_phases && prefetched != nx) {
             if (!more) __syncthreads();
             {
@@ -533,14 +551,14 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, buf0, buf1); else matvec_prefetch<CC_Q4_0>(s_next, buf0, buf1);
             prefetched = nx;
         }
-        if (more) { if (bvar == 0) grid_barrier_wait(bar, gen); else grid_barrier_wait_v1(bar, gridDim.x, gen, bvar == 2); gen++; }
+        if (more) { grid_barrier_wait(bar, gridDim.x, gen); gen++; }
     }
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases] = globaltimer_ns();
 }
 
 size_t cc_mega_smem_for_matvec(int type, int k) {
     size_t nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
-    return nbp * 32 + nbp * 4 + (type == CC_Q4_0 ? nbp * 4 : 0);
+    return nbp * 32 + nbp * 8 + 256;       // quants | scales | block sums | reduction scratch of the fused prologue
 }
 
 // developer hook: a table of `n` empty phases -> the pure per-phase floor (descriptor fetch + grid barrier)
