@@ -89,7 +89,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU path restated (oracle/), AVX2 order, all host threads, bounded sample
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 2):
+def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 3):
     from crabml_b200 import runner as R          # config table + byte accounting only (no GPU use)
     from oracle import oracle as oc
     from oracle.llama_replay import Llama2Runner, LlamaConfig, LlamaWeights
@@ -99,9 +99,23 @@ def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 2):
     cname, wt_name, ct_name = WORKLOADS[workload]
     conf = getattr(R, cname)
     wt, ct = TYPE_ID[wt_name], TYPE_ID[ct_name]
-    threads = oc.hw_threads()
-    dev = OracleDevice(thread_num=threads, flags=oc.ORDER_AVX2)
     dim, hid, kv = conf.embedding_dim, conf.hidden_dim, conf.head_size() * conf.n_kv_heads
+    # thread count: the reference takes it from the command line; use the count that is fastest for the dominant matvec on
+    # this host (ascending, stop when it gets slower -- oversubscribed spin-waiting workers are pathological on big hosts)
+    probe_w = synth_weight(wt, 2048, dim, SEED, 99, R.synth_scale(wt, dim))
+    probe_x = np.random.default_rng(0).standard_normal(dim).astype(np.float32)
+    threads, best = 1, float("inf")
+    for cand in sorted({c for c in (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128, oc.hw_threads()) if c <= oc.hw_threads()}):
+        oc.gemv(wt, probe_w, 2048, dim, probe_x, threads=cand, flags=oc.ORDER_AVX2)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            oc.gemv(wt, probe_w, 2048, dim, probe_x, threads=cand, flags=oc.ORDER_AVX2)
+        dt = time.perf_counter() - t0
+        if dt < best * 0.97:
+            threads, best = cand, dt
+        elif dt > best * 1.3:
+            break
+    dev = OracleDevice(thread_num=threads, flags=oc.ORDER_AVX2)
     n_sample_layers = min(2, conf.n_layers)
 
     def syn(rows, cols, t, tid):
@@ -126,18 +140,24 @@ def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 2):
                           w["ra"][:nl], w["rf"][:nl], norm(), out_w)
         r = Llama2Runner(OracleTensor, c, lw, dev, 16)
         r.forward([1], 0)                        # warm-up token
-        t0 = time.perf_counter()
+        best_t = float("inf")
         for i in range(budget_tokens):
+            t0 = time.perf_counter()
             r.forward([2 + i], 1 + i)
-        times[nl] = (time.perf_counter() - t0) / budget_tokens
+            best_t = min(best_t, time.perf_counter() - t0)
+        times[nl] = best_t
     if n_sample_layers > 1:
         per_layer = (times[n_sample_layers] - times[1]) / (n_sample_layers - 1)
+        if per_layer <= 0:                       # timer noise: split the 2-layer time by streamed bytes instead
+            lb = 4 * R.weight_bytes(wt, dim, dim) + 3 * R.weight_bytes(wt, hid, dim)
+            per_layer = times[n_sample_layers] * lb / (n_sample_layers * lb + R.weight_bytes(ct, conf.vocab_size, dim))
         rest = times[1] - per_layer
     else:
         per_layer, rest = times[1], 0.0
     per_token = per_layer * conf.n_layers + max(rest, 0.0)
     sample = (f"{n_sample_layers} of {conf.n_layers} layers + classifier of {workload} (same synthetic weights, seed {SEED:#x}), "
-              f"{budget_tokens} tokens after 1 warm-up, per-layer time x {conf.n_layers} + classifier; AVX2-order restatement, {threads} threads")
+              f"best of {budget_tokens} tokens after 1 warm-up, per-layer time x {conf.n_layers} + classifier; AVX2-order restatement, "
+              f"{threads} threads (fastest count of an ascending probe on this host, {oc.hw_threads()} hardware threads)")
     return 1.0 / per_token, threads, sample, per_token
 
 
@@ -170,8 +190,9 @@ def run_b200(args, rank, world, local_rank):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist_mod.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
+    sharded = world > 1 and args.multi == "sharded"
 
     def barrier():
         if dist is not None:
@@ -188,11 +209,24 @@ def run_b200(args, rank, world, local_rank):
     cname, wt_name, ct_name = WORKLOADS[args.workload]
     conf = getattr(R, cname)
     wt, ct = TYPE_ID[wt_name], TYPE_ID[ct_name]
-    dev = CudaTensorDevice(local_rank, lazy=args.lazy)
-    weights = R.synthetic_weights(dev, conf, wt, ct, seed=SEED)
+    transport = args.comm
+    lazy = args.lazy if not (sharded and transport == "nccl" and args.lazy == 2) else 1     # NCCL cannot run inside the megakernel
+    dev = CudaTensorDevice(local_rank, lazy=lazy)
+    plan = None
+    if sharded:
+        from crabml_b200 import sharding
+
+        def exchange(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+        plan = sharding.make_plan(conf.n_heads, conf.n_kv_heads, conf.embedding_dim, conf.hidden_dim, conf.vocab_size, wt, rank, world)
+        dev.init_comm(rank, world, exchange, transport)
+    args.lazy = lazy
+    weights = R.synthetic_weights(dev, conf, wt, ct, seed=SEED, plan=plan)
     K, W = args.steps, args.warmup
     kv_len = min(conf.seq_len, args.start_pos + 2 * (W + K) + 8)
-    runner = R.LlamaRunner(dev, conf, weights, kv_len)
+    runner = R.LlamaRunner(dev, conf, weights, kv_len, plan=plan)
     bytes_per_token = runner.weight_bytes_per_token()
 
     # context: fill the KV cache up to start_pos with untimed steps so that decode runs at a realistic position
@@ -234,7 +268,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel: ffn_gate/ffn_up-shaped matvec over all layers' weights (>> L2) ----------
     # (timed through an eager-mode device handle on the same GPU so that each matmul_vec is its own launch pair)
-    m, k = conf.hidden_dim, conf.embedding_dim
+    m, k = weights["ffn_gate"][0].shape()
     dev.synchronize()
     edev = CudaTensorDevice(local_rank, lazy=False) if args.lazy else dev
     x = CudaTensor.new(np.random.default_rng(1).standard_normal(k).astype(np.float32), [k], edev)
@@ -256,15 +290,20 @@ def run_b200(args, rank, world, local_rank):
     peaks, peak_src = measured_peaks()
 
     if rank == 0:
-        value = world * K / (val_ms * 1e-3)
-        e2e = world * K / (e2e_ms * 1e-3)
+        streams = 1 if sharded or world == 1 else world       # sharded: ONE token stream over N GPUs; replicas: N streams
+        value = streams * K / (val_ms * 1e-3)
+        e2e = streams * K / (e2e_ms * 1e-3)
         line = {
             "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": val_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+            "ms_per_step": val_ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}-decode-synthetic", "weights": wt_name, "classifier": ct_name, "kv_cache": "f32",
                        "start_pos": args.start_pos, "mode": {0: "eager (one launch per trait call)", 1: "lazy: fused kernels, CUDA-graph replay", 2: "lazy: one persistent megakernel per token, CUDA-graph replay"}[args.lazy],
-                       "multi_gpu": "independent replicas (row-sharded path: see DESIGN.md)" if world > 1 else "single GPU",
+                       "multi_gpu": ("single GPU" if world == 1 else
+                                     f"one token stream sharded over {world} GPUs: rows of wq/wk/wv/gate/up/classifier, block columns of wo/down; "
+                                     f"exchange = {'one-shot NVLink peer stores fused into the megakernel' if transport == 'p2p' and lazy == 2 else 'one-shot NVLink peer-store kernel' if transport == 'p2p' else 'ncclAllReduce/ncclAllGather'} "
+                                     f"(2 allreduce of [dim] f32 per layer + 1 allgather of logits)" if sharded else f"{world} independent replicas"),
+                       "weight_bytes_per_token_per_gpu": bytes_per_token,
                        "l2_policy": f"weights streamed once per token ({bytes_per_token / 1e9:.2f} GB >> 126 MB L2): inputs larger than L2",
                        "weight_bytes_per_token": bytes_per_token,
                        "hbm_frac_whole_step": bytes_per_token / (val_ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
@@ -301,6 +340,8 @@ def main():
     ap.add_argument("--start-pos", type=int, default=32, help="KV-cache length before the timed decode steps")
     ap.add_argument("--lazy", type=int, default=2, help="2 = record+fuse, one persistent megakernel per token (default); 1 = fused kernels in a CUDA graph; 0 = one launch per trait call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"], help="N > 1: shard one token stream (strong scaling, default) or run N independent replicas")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="exchange transport of the sharded path: one-shot NVLink peer stores (default) or the NCCL baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

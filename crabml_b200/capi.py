@@ -47,7 +47,7 @@ def declared_symbols():
 
 class ccr_llama_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_heads", "n_kv_heads", "n_layers", "embedding_dim", "hidden_dim", "seq_len", "vocab_size", "rope_dim")] + \
-               [("rms_norm_eps", C.c_float), ("use_f16_kv_cache", C.c_int32)]
+               [("rms_norm_eps", C.c_float), ("use_f16_kv_cache", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("hidden_local", C.c_int32)]
 
 
 class ccr_llama_weights(C.Structure):
@@ -112,6 +112,15 @@ def load_library(build_if_missing: bool = True):
         "cc_test_quantize_activation": (i32, [vp, pv, i32, vp, sz]),
         "cc_tensor_synth": (i32, [vp, C.POINTER(i64), i32, i32, u64, u64, f32, pp]),
         "cc_test_export_blocks": (i32, [vp, vp, vp, sz]),
+        "cc_tensor_synth_slice": (i32, [vp, C.POINTER(i64), i32, i32, u64, u64, f32, i64, i64, i64, i64, pp]),
+        "cc_comm_create": (i32, [vp, i32, i32, vp]),
+        "cc_comm_connect": (i32, [vp, vp]),
+        "cc_comm_nccl_unique_id": (i32, [vp, vp]),
+        "cc_comm_init_nccl": (i32, [vp, vp]),
+        "cc_comm_rank": (i32, [vp]),
+        "cc_comm_world_size": (i32, [vp]),
+        "cc_all_reduce_sum_inplace": (i32, [vp, pv]),
+        "cc_all_gather": (i32, [vp, pv, pv]),
         "cc_bench_timer_begin": (i32, [vp]),
         "cc_bench_timer_end": (i32, [vp, C.POINTER(f32)]),
     }

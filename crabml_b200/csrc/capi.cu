@@ -27,7 +27,7 @@ static bool view_ok(const cc_view* v) { return v && v->buf && v->ndim >= 1 && v-
         if (!view_ok(v)) return cc_fail((dev), CC_ERR_ARG, "%s: bad tensor view", what); \
     } while (0)
 // lazy mode (lazy.cu): after the same argument checks as eager mode the op is queued instead of launched
-enum { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU };
+enum { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU, L_ALLREDUCE, L_ALLGATHER };
 int cc_lazy_record(cc_device* dev, int kind, const cc_view* a, const cc_view* b, cc_buf* out, float f, int64_t i0, int64_t i1, int64_t i2,
                    const int64_t* rows, int n_rows);
 #define LAZY(dev) ((dev)->lz != nullptr && !(dev)->exact)
@@ -224,6 +224,31 @@ extern "C" CC_API int cc_scale_inplace(cc_device* dev, const cc_view* x, float r
     CC_REQUIRE(dev, view_contiguous(x), "scale_inplace: not contiguous");
     if (LAZY(dev)) return cc_lazy_record(dev, L_SCALE, x, nullptr, nullptr, rhs, 0, 0, 0, nullptr, 0);
     return cc_launch_scale(dev, (float*)x->buf->plane[0], view_len(x), rhs);
+}
+
+// ---- exchange step of the sharded path (comm.cu) ------------------------------------------------------------------------
+extern "C" CC_API int cc_all_reduce_sum_inplace(cc_device* dev, const cc_view* x) {
+    CHECK_VIEW(dev, x, "all_reduce_sum_inplace");
+    REQUIRE_F32(dev, x, "all_reduce_sum_inplace");
+    CC_REQUIRE(dev, view_contiguous(x), "all_reduce_sum_inplace: not contiguous");
+    CC_REQUIRE(dev, dev->comm, "all_reduce_sum_inplace: no communicator on this device");
+    const int64_t n = view_len(x);
+    CC_REQUIRE(dev, n % 4 == 0 && n <= CC_COMM_MAX_ELEMS, "all_reduce_sum_inplace: %lld elements unsupported", (long long)n);
+    if (LAZY(dev)) return cc_lazy_record(dev, L_ALLREDUCE, x, nullptr, nullptr, 0, n, 0, 0, nullptr, 0);
+    return cc_launch_all_reduce(dev, (float*)x->buf->plane[0], n, nullptr);
+}
+extern "C" CC_API int cc_all_gather(cc_device* dev, const cc_view* dst, const cc_view* src) {
+    CHECK_VIEW(dev, dst, "all_gather dst");
+    CHECK_VIEW(dev, src, "all_gather src");
+    REQUIRE_F32(dev, dst, "all_gather dst");
+    REQUIRE_F32(dev, src, "all_gather src");
+    CC_REQUIRE(dev, view_contiguous(dst) && view_contiguous(src), "all_gather: not contiguous");
+    CC_REQUIRE(dev, dev->comm, "all_gather: no communicator on this device");
+    const int64_t n = view_len(src);
+    CC_REQUIRE(dev, view_len(dst) == n * cc_comm_world(dev), "all_gather: dst has %lld elements, want %lld x %d", (long long)view_len(dst), (long long)n, cc_comm_world(dev));
+    CC_REQUIRE(dev, n % 4 == 0 && n <= CC_COMM_MAX_ELEMS, "all_gather: %lld elements per rank unsupported", (long long)n);
+    if (LAZY(dev)) return cc_lazy_record(dev, L_ALLGATHER, dst, src, nullptr, 0, n, 0, 0, nullptr, 0);
+    return cc_launch_all_gather(dev, (const float*)src->buf->plane[0], n, (float*)dst->buf->plane[0]);
 }
 
 // ---- matmul_vec: cpu_tensor.rs:371-386 + primitives/matmul_vec.rs:9-78 -------------------------------------------------

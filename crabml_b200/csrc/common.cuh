@@ -71,8 +71,20 @@ struct ActQ8_K {          // partner of all K-quants (buf_q8_k.rs:84-131)
     int16_t* bsums;       // [b][k/16]
 };
 
+// ---- comm.cu: exchange step of the sharded decode path ---------------------------------------------------
+#define CC_COMM_MAX_RANKS 8
+#define CC_COMM_MAX_ELEMS 32768          // f32 elements per exchange per rank (a [dim] row, or a vocab/N logit slice)
+struct CommDev {                         // by-value kernel argument: where every rank's window lives in THIS rank's address space
+    int rank, world;
+    float* data[CC_COMM_MAX_RANKS];      // data[p] + ((parity * 8 + src_rank) * CC_COMM_MAX_ELEMS)
+    unsigned* flag[CC_COMM_MAX_RANKS];   // flag[p][src_rank * 32]
+    unsigned* seq;                       // local: number of finished exchanges
+};
+struct cc_comm;
+
 struct cc_device {
     int ordinal = 0;
+    cc_comm* comm = nullptr;
     cudaStream_t stream = nullptr;
     bool debug_named_tensors = false;
     bool lazy = false;
@@ -192,7 +204,7 @@ struct StreamArgs {
     StreamMats mats;
     const void* act;         // ActQ8_0 scratch (quantize.cu layout) of k elements
     int k;
-    int epilogue;            // 0 store, 1 add residual, 2 silu(mat0 row) * (mat1 row)
+    int epilogue;            // 0 store, 1 add residual, 2 silu(mat0 row) * (mat1 row), 3 store into every rank's exchange slot (megakernel)
     const float* residual;
     const uint16_t* exp_lut;
 };
@@ -209,9 +221,10 @@ struct AttnArgs {            // fused decode attention (fused.cu)
 };
 struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; int64_t cols; };
 // megakernel phase descriptor (mega.cu); built by lazy.cu
-enum { MK_NORMQ = 0, MK_MATVEC = 1, MK_ATTN = 2, MK_ROWS = 3 };
+enum { MK_NORMQ = 0, MK_MATVEC = 1, MK_ATTN = 2, MK_ROWS = 3, MK_REDUCE = 4, MK_GATHER = 5 };
 struct MkPhase {
-    int type, wtype, write_back, next_matvec;   // next_matvec: index of the next MATVEC phase (look-ahead prefetch), -1 if none
+    int type, wtype, write_back, next_matvec;
+    int xgpu, red_n; float* red_dst; const float* red_res;   // cross-GPU barrier after this phase ; REDUCE/GATHER phase operands   // next_matvec: index of the next MATVEC phase (look-ahead prefetch), -1 if none
     // NORMQ (and the output quantisation of ATTN)
     float* x; float* orig; const float* norm_w; float eps; int n; ActQ8_0 act;
     StreamArgs mv;                      // MATVEC
@@ -220,8 +233,14 @@ struct MkPhase {
     DeqPlanes planes; int src_dtype, dst_dtype, n_rows, pad; long long cols; void* dst;   // ROWS
 };
 size_t cc_mega_smem_for_matvec(int type, int k);
+const CommDev* cc_comm_dev(cc_device* dev);
+bool cc_comm_is_nccl(cc_device* dev);
+int cc_comm_world(cc_device* dev);
+void cc_comm_destroy(cc_device* dev);
+int cc_launch_all_reduce(cc_device* dev, float* x, int64_t n, const float* residual);
+int cc_launch_all_gather(cc_device* dev, const float* src, int64_t n, float* dst);
 extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase);
-int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof);
+int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof, const CommDev* comm);
 int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch, bool write_back);
 int cc_launch_attn_decode(cc_device* dev, const AttnArgs& a);
 struct LazyState;
@@ -266,6 +285,12 @@ __device__ __forceinline__ int4 ld_stream_16(const void* p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+}
+__device__ __forceinline__ void cc_st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned cc_ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ float h2f_bits(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 __device__ __forceinline__ uint16_t f2h_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }

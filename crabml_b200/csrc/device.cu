@@ -101,6 +101,7 @@ extern "C" CC_API void cc_device_destroy(cc_device* dev) {
     cudaSetDevice(dev->ordinal);
     cudaStreamSynchronize(dev->stream);
     cc_lazy_destroy(dev);
+    cc_comm_destroy(dev);
     for (auto& kv : dev->free_lists)
         for (uintptr_t p : kv.second) cudaFree((void*)p);
     if (dev->act_scratch) cudaFree(dev->act_scratch);
@@ -311,6 +312,48 @@ extern "C" CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int3
     cudaError_t e2 = cudaStreamSynchronize(dev->stream);
     if (dev->exact) b->raw = staging; else cudaFree(staging);
     if (rc == CC_OK && e2 != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "synth: %s", cudaGetErrorString(e2));
+    if (rc != CC_OK) { cudaFree(b->base); if (b->raw) cudaFree(b->raw); delete b; return rc; }
+    *out = b;
+    return CC_OK;
+}
+
+// Shard of a synthetic matrix: the full tensor is generated (same counter-based bytes as cc_tensor_synth), then the
+// requested rows x block-columns are compacted and repacked.  Rows shard wq/wk/wv/gate/up/classifier, columns shard wo/down.
+extern "C" CC_API int cc_tensor_synth_slice(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t t, uint64_t seed, uint64_t tensor_id,
+                                            float scale, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, cc_buf** out) {
+    if (!dev || !shape || !out || ndim != 2) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_synth_slice: bad argument (2-d tensors only)");
+    int be = cc_block_elems(t);
+    CC_REQUIRE(dev, be > 1, "synth_slice: quantized types only, got %d", t);
+    const int64_t rows = shape[0], cols = shape[1];
+    CC_REQUIRE(dev, cols % be == 0 && col0 % be == 0 && ncols % be == 0, "synth_slice: columns must be multiples of the %d-element block", be);
+    CC_REQUIRE(dev, row0 >= 0 && nrows > 0 && row0 + nrows <= rows && col0 >= 0 && ncols > 0 && col0 + ncols <= cols, "synth_slice: slice out of range");
+    const size_t bb = cc_block_bytes(t);
+    const size_t full = (size_t)(rows * cols / be) * bb, part = (size_t)(nrows * ncols / be) * bb;
+    cc_buf* b = new cc_buf();
+    b->dev = dev; b->dtype = t; b->nelems = nrows * ncols; b->rows = nrows; b->cols = ncols;
+    b->bytes = cc_device_layout_bytes(t, nrows, ncols);
+    uint8_t *staging = nullptr, *compact = nullptr;
+    cudaError_t e = cudaMalloc(&b->base, b->bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&staging, full);
+    if (e == cudaSuccess) e = cudaMalloc(&compact, part);
+    if (e != cudaSuccess) {
+        if (b->base) cudaFree(b->base);
+        if (staging) cudaFree(staging);
+        delete b;
+        return cc_fail(dev, CC_ERR_CUDA, "synth_slice alloc: %s", cudaGetErrorString(e));
+    }
+    cc_assign_planes(b);
+    int rc = cc_launch_synth(dev, staging, t, rows * cols / be, seed, tensor_id, scale);
+    if (rc == CC_OK) {
+        const size_t row_bytes = (size_t)(cols / be) * bb, w = (size_t)(ncols / be) * bb;
+        e = cudaMemcpy2DAsync(compact, w, staging + (size_t)row0 * row_bytes + (size_t)(col0 / be) * bb, row_bytes, w, (size_t)nrows, cudaMemcpyDeviceToDevice, dev->stream);
+        if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "synth_slice compact: %s", cudaGetErrorString(e));
+    }
+    if (rc == CC_OK) rc = cc_launch_repack(dev, compact, b);
+    cudaError_t e2 = cudaStreamSynchronize(dev->stream);
+    cudaFree(staging);
+    if (dev->exact) b->raw = compact; else cudaFree(compact);
+    if (rc == CC_OK && e2 != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "synth_slice: %s", cudaGetErrorString(e2));
     if (rc != CC_OK) { cudaFree(b->base); if (b->raw) cudaFree(b->raw); delete b; return rc; }
     *out = b;
     return CC_OK;

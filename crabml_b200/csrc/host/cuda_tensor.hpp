@@ -157,6 +157,10 @@ public:
     CudaTensor add_inplace(const CudaTensor& rhs) && { cc_view v = view(), r = rhs.view(); check(dev_, cc_add_inplace(dev_, &v, &r)); return std::move(*this); }
     CudaTensor scale_inplace(float s) && { cc_view v = view(); check(dev_, cc_scale_inplace(dev_, &v, s)); return std::move(*this); }
 
+    // ---- exchange step of the sharded path (not in the reference's trait: it is single-device; crabml_cuda.h) ------------
+    CudaTensor all_reduce_sum_inplace() && { cc_view v = view(); check(dev_, cc_all_reduce_sum_inplace(dev_, &v)); return std::move(*this); }
+    void all_gather_from(const CudaTensor& slice) { cc_view d = view(), s = slice.view(); check(dev_, cc_all_gather(dev_, &d, &s)); }
+
     // ---- hot path (api.rs:76-78) -----------------------------------------------------------------------------------
     CudaTensor matmul_vec(const CudaTensor& x) const {
         cc_view w = view(), xv = x.view();

@@ -21,6 +21,12 @@ struct ccr_runner {
     std::vector<float> logits;
     std::string last_error;
 
+    // Sharded decode.  shard_world > 1: this process holds heads [rank*H/N, (rank+1)*H/N) of wq/wk/wv (rows), the
+    // matching COLUMNS of wo, hidden_local rows of gate/up and columns of down, vocab/N rows of the classifier; the replay is
+    // the reference's op order with one all_reduce_sum after wo and after ffn_down and one all_gather of the logits.
+    int world() const { return conf.shard_world > 1 ? conf.shard_world : 1; }
+    int local_heads() const { return conf.n_heads / world(); }
+    int local_kv_heads() const { return conf.n_kv_heads / world(); }
     int head_size() const { return conf.embedding_dim / conf.n_heads; }
     int64_t kv_cache_len() const { return key_cache[0].shape()[1]; }
 
@@ -37,13 +43,18 @@ void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float*
     x_final.copy_rows_from(x, {(int64_t)tokens.size() - 1});
     const CudaTensor& ow = output_weight.valid() ? output_weight : token_embed;
     CudaTensor lg = ow.matmul_vec(x_final);
+    if (world() > 1) {                                   // row-split classifier: gather the vocab/N slices
+        CudaTensor full = CudaTensor::alloc({conf.vocab_size}, CC_F32, dev);
+        full.all_gather_from(lg);
+        lg = std::move(full);
+    }
     if (logits_out) lg.export_to(logits_out, (size_t)conf.vocab_size);
     else CudaTensor::check(dev, cc_device_flush(dev));     // lazy mode: submit this token's work without a host sync
 }
 
 // llama2.rs:213-281
 CudaTensor ccr_runner::forward_llama(const std::vector<int64_t>& tokens, int64_t pos) {
-    const int64_t embed_dim = conf.embedding_dim, n_heads = conf.n_heads, n_kv_heads = conf.n_kv_heads;
+    const int64_t embed_dim = conf.embedding_dim, n_heads = local_heads(), n_kv_heads = local_kv_heads();
     const int64_t head_dim = head_size();
     const int64_t rope_dim = conf.rope_dim > 0 ? conf.rope_dim : head_dim;
     const int64_t n_batch = (int64_t)tokens.size();
@@ -68,6 +79,7 @@ CudaTensor ccr_runner::forward_llama(const std::vector<int64_t>& tokens, int64_t
         k = std::move(k).rope_inplace(CC_ROPE_LLAMA, pos, rope_dim);
 
         x = forward_multi_query_attention(std::move(q), std::move(k), std::move(v), l, n_batch);
+        if (world() > 1) x = std::move(x).all_reduce_sum_inplace();      // column-split wo: sum the [dim] partials
         x = std::move(x).with_name("attn_out:" + std::to_string(l) + ":" + std::to_string(pos));
         x = std::move(x).add_inplace(x_attn_orig);
         x = forward_ffn(std::move(x), l);
@@ -80,7 +92,7 @@ CudaTensor ccr_runner::forward_llama(const std::vector<int64_t>& tokens, int64_t
 
 // llama2.rs:527-603
 CudaTensor ccr_runner::forward_multi_query_attention(CudaTensor q, CudaTensor k, CudaTensor v, int l, int64_t n_batch) {
-    const int64_t n_heads = conf.n_heads, n_kv_heads = conf.n_kv_heads, head_dim = head_size(), embed_dim = conf.embedding_dim;
+    const int64_t n_heads = local_heads(), n_kv_heads = local_kv_heads(), head_dim = head_size(), embed_dim = n_heads * head_dim;
     {
         CudaTensor kt = std::move(k).reshape({n_batch, n_kv_heads, head_dim}).transpose({1, 0, 2});
         CudaTensor vt = std::move(v).reshape({n_batch, n_kv_heads, head_dim}).transpose({1, 0, 2});
@@ -115,6 +127,7 @@ CudaTensor ccr_runner::forward_ffn(CudaTensor x, int l) {
     h1 = std::move(h1).silu_inplace();
     h1 = std::move(h1).mul_inplace(h2);
     x = ffn_down[l].matmul_vec(h1);
+    if (world() > 1) x = std::move(x).all_reduce_sum_inplace();          // column-split ffn_down
     x = std::move(x).add_inplace(x_orig_ffn);
     return x;
 }
@@ -147,15 +160,26 @@ extern "C" CC_API int ccr_runner_create(cc_device* dev, const ccr_llama_config* 
     r->dev = dev;
     r->conf = *conf;
     int rc = guarded(r, [&] {
-        const int64_t dim = conf->embedding_dim, hidden = conf->hidden_dim, hd = dim / conf->n_heads, kv_dim = hd * conf->n_kv_heads;
+        const int N = r->world();
+        const int64_t dim = conf->embedding_dim, hd = dim / conf->n_heads;
+        const int64_t q_dim = hd * r->local_heads(), kv_dim = hd * r->local_kv_heads();
+        const int64_t hidden = N > 1 ? conf->hidden_local : conf->hidden_dim, vocab_rows = conf->vocab_size / N;
+        if (N > 1) {
+            if (conf->n_heads % N || conf->n_kv_heads % N || conf->vocab_size % N) throw crabml::TensorError("sharding: heads / kv heads / vocab must divide by the world size");
+            // the F32-cache attention of the reference pairs query head h with kv head h % n_kv (batch_matmul.rs:47-71, quirk B13):
+            // contiguous head ranges keep that mapping local only without grouping
+            if (conf->n_heads != conf->n_kv_heads && !conf->use_f16_kv_cache) throw crabml::TensorError("sharding: grouped-query models need the f16 kv cache (contiguous kv groups)");
+            if (!w->output_weight) throw crabml::TensorError("sharding: tied classifier is not supported (pass a row shard as output_weight)");
+            if (hidden <= 0) throw crabml::TensorError("sharding: hidden_local missing");
+        }
         r->token_embed = CudaTensor::wrap(dev, w->token_embed, {conf->vocab_size, dim});
         r->rms_final = CudaTensor::wrap(dev, w->rms_final, {dim});
-        if (w->output_weight) r->output_weight = CudaTensor::wrap(dev, w->output_weight, {conf->vocab_size, dim});
+        if (w->output_weight) r->output_weight = CudaTensor::wrap(dev, w->output_weight, {vocab_rows, dim});
         for (int l = 0; l < conf->n_layers; l++) {
-            r->wq.push_back(CudaTensor::wrap(dev, w->wq[l], {dim, dim}));
+            r->wq.push_back(CudaTensor::wrap(dev, w->wq[l], {q_dim, dim}));
             r->wk.push_back(CudaTensor::wrap(dev, w->wk[l], {kv_dim, dim}));
             r->wv.push_back(CudaTensor::wrap(dev, w->wv[l], {kv_dim, dim}));
-            r->wo.push_back(CudaTensor::wrap(dev, w->wo[l], {dim, dim}));
+            r->wo.push_back(CudaTensor::wrap(dev, w->wo[l], {dim, q_dim}));
             r->ffn_gate.push_back(CudaTensor::wrap(dev, w->ffn_gate[l], {hidden, dim}));
             r->ffn_down.push_back(CudaTensor::wrap(dev, w->ffn_down[l], {dim, hidden}));
             r->ffn_up.push_back(CudaTensor::wrap(dev, w->ffn_up[l], {hidden, dim}));
@@ -163,8 +187,8 @@ extern "C" CC_API int ccr_runner_create(cc_device* dev, const ccr_llama_config* 
             r->rms_ffn.push_back(CudaTensor::wrap(dev, w->rms_ffn[l], {dim}));
             // llama2.rs:65-86: pre-allocated [n_kv_heads, seq_len, head_dim], resized to length 0
             int kvt = conf->use_f16_kv_cache ? CC_F16 : CC_F32;
-            r->key_cache.push_back(CudaTensor::alloc({conf->n_kv_heads, kv_seq_len, hd}, kvt, dev).resize(1, 0));
-            r->value_cache.push_back(CudaTensor::alloc({conf->n_kv_heads, kv_seq_len, hd}, kvt, dev).resize(1, 0));
+            r->key_cache.push_back(CudaTensor::alloc({r->local_kv_heads(), kv_seq_len, hd}, kvt, dev).resize(1, 0));
+            r->value_cache.push_back(CudaTensor::alloc({r->local_kv_heads(), kv_seq_len, hd}, kvt, dev).resize(1, 0));
         }
         r->logits.assign((size_t)conf->vocab_size, 0.0f);
     });

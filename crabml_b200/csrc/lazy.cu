@@ -21,7 +21,7 @@
 
 #include "common.cuh"
 
-enum LKind { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU };
+enum LKind { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU, L_ALLREDUCE, L_ALLGATHER };
 
 struct LView { cc_buf* buf = nullptr; int ndim = 0; int64_t shape[CC_MAX_DIMS] = {0, 0, 0, 0}, strides[CC_MAX_DIMS] = {0, 0, 0, 0}; };
 
@@ -182,6 +182,8 @@ struct Fuser {
             case L_SCALE: return cc_launch_scale(d, (float*)a.buf->plane[0], vlen(a), op.f);
             case L_SILU: return cc_launch_silu(d, (float*)a.buf->plane[0], vlen(a));
             case L_GELU: return cc_launch_gelu(d, (float*)a.buf->plane[0], vlen(a));
+            case L_ALLREDUCE: return cc_launch_all_reduce(d, (float*)a.buf->plane[0], op.i0, nullptr);
+            case L_ALLGATHER: return cc_launch_all_gather(d, (const float*)b.buf->plane[0], op.i0, (float*)a.buf->plane[0]);
             case L_SOFTMAX: { int64_t cols = a.shape[a.ndim - 1]; return cc_launch_softmax(d, (float*)a.buf->plane[0], cols ? vlen(a) / cols : 0, cols); }
             case L_ROPE: return cc_launch_rope_exact(d, (float*)a.buf->plane[0], op.i1, op.i2, a.shape[a.ndim - 1], (int)op.f, op.i0, op.rows[0]);
             case L_CONCAT:
@@ -278,6 +280,17 @@ struct Fuser {
         } else if (n > 1 && is(i + n, L_SILU)) {
             n = 1; used = 1;                   // do not swallow a gate/up pair we could not fuse as a pair
         }
+        // sharded path: column-split matvec -> allreduce [-> + residual]  /  row-split classifier -> allgather (comm.cu)
+        int xchg = 0; float* xdst = nullptr; const float* xres = nullptr;
+        if (A.epilogue == 0 && is(i + 1, L_ALLREDUCE) && q[i + 1].a.buf == m0.out && q[i + 1].i0 == m0.a.shape[0]) {
+            n = 1; xchg = 1; used = 2; xdst = (float*)m0.out->base;
+            if (is(i + 2, L_ADD) && q[i + 2].a.buf == m0.out && vlen(q[i + 2].b) == m0.a.shape[0] && q[i + 2].b.buf->dtype == CC_F32 && vcontig(q[i + 2].b)) {
+                xres = (const float*)q[i + 2].b.buf->plane[0];
+                used = 3;
+            }
+        } else if (A.epilogue == 0 && is(i + 1, L_ALLGATHER) && q[i + 1].b.buf == m0.out && q[i + 1].i0 == m0.a.shape[0]) {
+            n = 1; xchg = 2; used = 2; xdst = (float*)q[i + 1].a.buf->plane[0];
+        }
         A.mats.n = (int)n;
         for (size_t t = 0; t < n; t++) {
             A.mats.qs[t] = q[i + t].a.buf->plane[0];
@@ -297,7 +310,17 @@ struct Fuser {
         P.S(0x2003); P.S(wt); P.S(k); P.S(A.epilogue); P.SP(A.residual); P.SP(act);
         for (size_t t = 0; t < n; t++) { P.SP(A.mats.qs[t]); P.SP(A.mats.out[t]); P.S(A.mats.m[t]); }
         P.steps.push_back([=](uint8_t*) { return cc_launch_matvec_stream(d, wt, A); });
-        { MkPhase ph = {}; ph.type = MK_MATVEC; ph.wtype = wt; ph.mv = A; P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_matvec(wt, (int)k)); }
+        { MkPhase ph = {}; ph.type = MK_MATVEC; ph.wtype = wt; ph.mv = A; if (xchg) { ph.mv.epilogue = 3; ph.xgpu = 1; }
+          P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_matvec(wt, (int)k)); }
+        if (xchg) {
+            const int64_t mrows = m0.a.shape[0];
+            float* part = A.mats.out[0];
+            P.S(0x2006); P.S(xchg); P.SP(xdst); P.SP(xres); P.S(mrows);
+            if (xchg == 1) P.steps.push_back([=](uint8_t*) { return cc_launch_all_reduce(d, part, mrows, xres); });
+            else P.steps.push_back([=](uint8_t*) { return cc_launch_all_gather(d, part, mrows, xdst); });
+            MkPhase ph = {}; ph.type = xchg == 1 ? MK_REDUCE : MK_GATHER; ph.red_n = (int)mrows; ph.red_dst = xdst; ph.red_res = xres; P.phases.push_back(ph);
+            if (!cc_comm_dev(dev) || cc_comm_is_nccl(dev)) P.mega_ok = false;      // NCCL baseline: graph of kernels + NCCL nodes (lazy mode 1)
+        }
         for (size_t t = i; t < i + used; t++) q[t].done = true;
         return used;
     }
@@ -498,7 +521,7 @@ int cc_lazy_flush(cc_device* dev) {
                 if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue : 0)); }
                 if (use_mega) cudaMemsetAsync(lz->bar_dev, 0, 4096, dev->stream);      // (captured) barrier counters restart from 0 in every replay
                 rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem,
-                                               P.phases.size() < 4000 ? lz->prof_dev : nullptr) : run_steps(lz->dyn_dev);
+                                               P.phases.size() < 4000 ? lz->prof_dev : nullptr, cc_comm_dev(dev)) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);
                 if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: end capture: %s", cudaGetErrorString(e));
             }

@@ -40,15 +40,26 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm vo
 // at the head of every graph replay, so `gen` starts at 0.
 __device__ __forceinline__ void red_add_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 #define MK_BAR_THREAD (MK_THREADS - 1)
-__device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen) {
+__device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen, bool xgpu = false) {
     __syncthreads();
-    if (threadIdx.x == MK_BAR_THREAD) red_add_release(&bar[0], 1u);
+    if (threadIdx.x == MK_BAR_THREAD) {
+        if (xgpu) __threadfence_system();          // this CTA's stores into the peers' exchange slots precede its arrival
+        red_add_release(&bar[0], 1u);
+    }
 }
-__device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblocks, unsigned gen) {
+// xseq != 0: the barrier doubles as the handshake of exchange number xseq with the other GPUs (protocol: comm.cu).  CTA 0's
+// barrier thread, once every local CTA has arrived (all partial rows are stored in the peers' slots), publishes xseq in each
+// peer's flag word, waits for every peer's xseq in its own flag words, and only then opens the local barrier.
+__device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblocks, unsigned gen, const CommDev& comm, unsigned xseq = 0) {
     if (threadIdx.x == MK_BAR_THREAD) {
         if (blockIdx.x == 0) {
             const unsigned target = (gen + 1u) * nblocks;
             while (ld_acquire_u32(&bar[0]) != target) { }
+            if (xseq) {
+                __threadfence_system();
+                for (int p = 0; p < comm.world; p++) cc_st_release_sys(comm.flag[p] + comm.rank * 32, xseq);
+                for (int p = 0; p < comm.world; p++) { const unsigned* f = comm.flag[comm.rank] + p * 32; while ((int)(cc_ld_acquire_sys(f) - xseq) < 0) { } }
+            }
             st_release_u32(&bar[32], gen + 1u);
         } else {
             while (ld_acquire_u32(&bar[32]) != gen + 1u) { }
@@ -208,7 +219,7 @@ __device__ __forceinline__ void matvec_prefetch(const StreamArgs& A, MkSeg& buf0
 
 // precondition: buf0 / buf1 hold this warp's segments 0 / 1 (matvec_prefetch)
 template <int TYPE>
-__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut, MkSeg& buf0, MkSeg& buf1) {
+__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut, MkSeg& buf0, MkSeg& buf1, const CommDev& comm, unsigned xseq) {
     const StreamArgs& A = ph.mv;
     const int k = A.k;
     const MkGeo g = mk_geo(A);
@@ -230,23 +241,27 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         // Fused prologue: [rms_norm * w] + Q8_0 quantisation of x, computed by EVERY CTA straight into its shared memory
         // (redundant across SMs, ~1.5 us of issue time) -- cheaper than a separate NORMQ phase, which costs a grid barrier
         // (~2.1 us) plus its own latency chain.  The weight segments requested by matvec_prefetch are in flight meanwhile.
-        const float* x = ph.x;
         const int n = k;
         const int warp = threadIdx.x >> 5;
+        float* s_red = (float*)(smem + (size_t)nbp * 40);                // scratch behind the activation arrays
+        float* s_x = s_red + 64;                                          // f32 copy of x, then of the norm weights
+        float* s_w = s_x + n;
+        {   // one L2 round trip: every 16-byte chunk of x (and of the norm weights) requested at once with cp.async.cg
+            const int n4 = n >> 2;
+            const unsigned sx = (unsigned)__cvta_generic_to_shared(s_x), sw = (unsigned)__cvta_generic_to_shared(s_w);
+            for (int i = threadIdx.x; i < n4; i += MK_THREADS) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 16), "l"(ph.x + i * 4) : "memory");
+                if (ph.norm_w) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sw + i * 16), "l"(ph.norm_w + i * 4) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
         float rms = 1.0f;
         if (ph.norm_w) {
             float ss = 0.0f;
-            const float4* x4 = (const float4*)x;
-            const int n4 = n >> 2;
-            for (int i0 = 0; i0 < n4; i0 += MK_THREADS * 4) {
-                float4 v[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) { int i = i0 + j * MK_THREADS + threadIdx.x; v[j] = i < n4 ? __ldcg(x4 + i) : make_float4(0, 0, 0, 0); }
-#pragma unroll
-                for (int j = 0; j < 4; j++) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
-            }
+            const float4* x4 = (const float4*)s_x;
+            for (int i = threadIdx.x; i < (n >> 2); i += MK_THREADS) { float4 v = x4[i]; ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
             ss = warp_sum(ss);
-            float* s_red = (float*)(smem + (size_t)nbp * 32 + (size_t)nbp * 8);     // scratch behind the activation arrays
             if (lane == 0) s_red[warp] = ss;
             __syncthreads();
             float t = 0.0f;
@@ -255,24 +270,16 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
             rms = sqrtf(t / (float)n + ph.eps);
         }
         if (ph.orig && blockIdx.x == 0)                              // Tensor::dup of the un-normalised row (llama2.rs:227,607)
-            for (int i = threadIdx.x; i < n; i += MK_THREADS) ph.orig[i] = ldcg_f(x + i);
-        for (int b0 = 0; b0 < nbp; b0 += MK_WARPS * 4) {             // 4 blocks per warp per pass, loads first
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) { const int b = b0 + j * MK_WARPS + warp; v[j] = b < nb ? ldcg_f(x + b * 32 + lane) : 0.0f; }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int b = b0 + j * MK_WARPS + warp;
-                if (b >= nbp) continue;
-                float xv = v[j];
-                if (ph.norm_w && b < nb) xv = (xv / rms) * ph.norm_w[b * 32 + lane];
-                float amax = warp_max(fabsf(xv));
-                float d = amax / 127.0f;
-                int q = b < nb ? __float2int_rz(xv / d) : 0;
-                s_q[b * 32 + lane] = (int8_t)q;
-                if constexpr (TYPE == CC_Q4_0) { int sq = warp_sum_i(q); if (lane == 0) s_s[b] = sq; }
-                if (lane == 0) s_d[b] = b < nb ? __half2float(__float2half_rn(d)) : 0.0f;
-            }
+            for (int i = threadIdx.x; i < n; i += MK_THREADS) ph.orig[i] = s_x[i];
+        for (int b = warp; b < nbp; b += MK_WARPS) {
+            float xv = b < nb ? s_x[b * 32 + lane] : 0.0f;
+            if (ph.norm_w && b < nb) xv = (xv / rms) * s_w[b * 32 + lane];
+            float amax = warp_max(fabsf(xv));
+            float d = amax / 127.0f;
+            int q = b < nb ? __float2int_rz(xv / d) : 0;
+            s_q[b * 32 + lane] = (int8_t)q;
+            if constexpr (TYPE == CC_Q4_0) { int sq = warp_sum_i(q); if (lane == 0) s_s[b] = sq; }
+            if (lane == 0) s_d[b] = b < nb ? __half2float(__float2half_rn(d)) : 0.0f;
         }
     } else {   // stage the quantised activation (written by other CTAs in the previous phase: L2 loads)
         const uint8_t* act = (const uint8_t*)A.act;
@@ -311,6 +318,11 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
             int mat = 0, rr = gw + i * TW;
             if (M.n > 1 && rr >= M.m[0]) { rr -= M.m[0]; mat = 1; if (M.n > 2 && rr >= M.m[1]) { rr -= M.m[1]; mat = 2; } }
             if (A.epilogue == 1) r = r + ldcg_f(A.residual + rr);
+            if (A.epilogue == 3) {         // partial row -> slot[rank] of every GPU's exchange window (NVLink peer stores)
+                const size_t off = ((size_t)((xseq + 1u) & 1u) * CC_COMM_MAX_RANKS + comm.rank) * CC_COMM_MAX_ELEMS + rr;
+                for (int pr = 0; pr < comm.world; pr++) comm.data[pr][off] = r;
+                return;
+            }
             float* o = mat == 0 ? M.out[0] : mat == 1 ? M.out[1] : M.out[2];
             o[rr] = r;
         }
@@ -490,6 +502,29 @@ __device__ void phase_rows(const MkPhase& ph, const uint8_t* dyn) {
     }
 }
 
+// ---- REDUCE / GATHER phases: second half of an exchange (the first half is epilogue 3 of the MATVEC phase + the handshake
+// carried by its barrier).  REDUCE: dst = sum over ranks of the partial rows, rank order, (+ residual)   GATHER: dst = slices
+__device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsigned xseq, bool gather) {
+    const float* base = comm.data[comm.rank] + (size_t)(xseq & 1u) * CC_COMM_MAX_RANKS * CC_COMM_MAX_ELEMS;
+    const int n4 = ph.red_n >> 2;
+    if (gather) {
+        for (int i = blockIdx.x * MK_THREADS + threadIdx.x; i < n4 * comm.world; i += gridDim.x * MK_THREADS) {
+            const int p = i / n4, j = i - p * n4;
+            ((float4*)(ph.red_dst + (size_t)p * ph.red_n))[j] = __ldcg((const float4*)(base + (size_t)p * CC_COMM_MAX_ELEMS) + j);
+        }
+        return;
+    }
+    for (int i = blockIdx.x * MK_THREADS + threadIdx.x; i < n4; i += gridDim.x * MK_THREADS) {
+        float4 a = __ldcg((const float4*)base + i);
+        for (int p = 1; p < comm.world; p++) {
+            const float4 b = __ldcg((const float4*)(base + (size_t)p * CC_COMM_MAX_ELEMS) + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        if (ph.red_res) { const float4 r = __ldcg((const float4*)ph.red_res + i); a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+        ((float4*)ph.red_dst)[i] = a;
+    }
+}
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -497,7 +532,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
-                                                                         unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags) {
+                                                                         unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags, const CommDev comm) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float s_red[MK_WARPS];
     __shared__ MkPhase s_phs[2];             // phase descriptors, double-buffered: p+1 is fetched while p runs
@@ -507,6 +542,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     int prefetched = -1;                     // phase index whose first two segments sit in buf0 / buf1
     unsigned gen = 0;                        // barriers completed; starts from the value left by the last launch
     if (threadIdx.x == MK_BAR_THREAD) gen = ld_acquire_u32(&bar[32]);
+    unsigned xseq = comm.world > 0 ? *comm.seq : 0u;     // exchanges finished so far on this rank (comm.cu)
     auto fetch_desc = [&](int p) {
         const int* src = (const int*)(phases + p);
         int* dst = (int*)&s_phs[p & 1];
@@ -523,22 +559,25 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         case MK_MATVEC:
             if (s_ph.wtype == CC_Q8_0) {
                 if (prefetched != p) matvec_prefetch<CC_Q8_0>(s_ph.mv, buf0, buf1);
-                phase_matvec<CC_Q8_0>(s_ph, smem, exp_lut, buf0, buf1);
+                phase_matvec<CC_Q8_0>(s_ph, smem, exp_lut, buf0, buf1, comm, xseq);
             } else {
                 if (prefetched != p) matvec_prefetch<CC_Q4_0>(s_ph.mv, buf0, buf1);
-                phase_matvec<CC_Q4_0>(s_ph, smem, exp_lut, buf0, buf1);
+                phase_matvec<CC_Q4_0>(s_ph, smem, exp_lut, buf0, buf1, comm, xseq);
             }
             break;
         case MK_ATTN:
             if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)smem, s_red, dyn, exp_lut); else phase_attn<false>(s_ph, (float*)smem, s_red, dyn, exp_lut);
             break;
         case MK_ROWS: phase_rows(s_ph, dyn); break;
+        case MK_REDUCE: phase_reduce(s_ph, comm, xseq, false); break;
+        case MK_GATHER: phase_reduce(s_ph, comm, xseq, true); break;
         }
         // look-ahead: request the first two weight segments of the next MATVEC phase before waiting at the barrier, so HBM
         // keeps streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
         const int nx = s_ph.next_matvec;
         const bool more = p + 1 < n_phases;
-        if (more) grid_barrier_arrive(bar, gridDim.x, gen);
+        const bool xg = s_ph.xgpu != 0;
+        if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);
         if ((flags & 1) && nx > p && nx < n_phases && prefetched != nx) {
             if (!more) __syncthreads();
             {
@@ -551,14 +590,15 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, buf0, buf1); else matvec_prefetch<CC_Q4_0>(s_next, buf0, buf1);
             prefetched = nx;
         }
-        if (more) { grid_barrier_wait(bar, gridDim.x, gen); gen++; }
+        if (more) { grid_barrier_wait(bar, gridDim.x, gen, comm, xg ? xseq + 1u : 0u); gen++; if (xg) xseq++; }
     }
+    if (comm.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) *comm.seq = xseq;
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases] = globaltimer_ns();
 }
 
 size_t cc_mega_smem_for_matvec(int type, int k) {
     size_t nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
-    return nbp * 32 + nbp * 8 + 256;       // quants | scales | block sums | reduction scratch of the fused prologue
+    return nbp * 40 + 256 + (size_t)k * 8;  // quants | scales | block sums | prologue: reduction scratch, f32 x, f32 norm weights
 }
 
 // developer hook: a table of `n` empty phases -> the pure per-phase floor (descriptor fetch + grid barrier)
@@ -576,7 +616,7 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
     for (int rep = 0; rep < 4; rep++) {
         CC_CUDA(dev, cudaMemsetAsync(d_bar, 0, 4096, dev->stream));
         cudaEventRecord(e0, dev->stream);
-        int rc = cc_launch_mega(dev, d_tab, n, nullptr, d_bar, 1024, nullptr);
+        int rc = cc_launch_mega(dev, d_tab, n, nullptr, d_bar, 1024, nullptr, nullptr);
         if (rc) return rc;
         cudaEventRecord(e1, dev->stream);
         CC_CUDA(dev, cudaEventSynchronize(e1));
@@ -588,7 +628,7 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
     return CC_OK;
 }
 
-int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof) {
+int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof, const CommDev* comm) {
     static const int flags = (getenv("CRABML_MEGA_NOPREFETCH") ? 0 : 1) | (getenv("CRABML_MEGA_FLAGS") ? atoi(getenv("CRABML_MEGA_FLAGS")) : 0);     // developer A/B switches
     int max_ctas_per_sm = 0;
     if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -596,7 +636,10 @@ int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, cons
     CC_REQUIRE(dev, max_ctas_per_sm >= 1, "megakernel does not fit on an SM");
     int per_sm = max_ctas_per_sm < MK_CTAS_PER_SM ? max_ctas_per_sm : MK_CTAS_PER_SM;
     int grid = dev->sm_count * per_sm;          // all CTAs co-resident: required by the grid barrier
-    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut, prof, flags);
+    CommDev cd;
+    memset(&cd, 0, sizeof(cd));
+    if (comm) cd = *comm;
+    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut, prof, flags, cd);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }

@@ -8,7 +8,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from . import capi
+from . import capi, sharding
 from .capi import CudaError, TensorError
 from .tensor import CudaTensor, CudaTensorDevice
 
@@ -45,11 +45,14 @@ def weight_bytes(dtype, rows, cols):
 
 
 class LlamaRunner:
-    def __init__(self, device: CudaTensorDevice, conf: LlamaConfig, weights: dict, kv_seq_len: int, f16_kv: bool = False):
-        self.device, self.conf, self.weights = device, conf, weights          # keep the tensors alive
+    def __init__(self, device: CudaTensorDevice, conf: LlamaConfig, weights: dict, kv_seq_len: int, f16_kv: bool = False,
+                 plan: "sharding.ShardPlan | None" = None):
+        """plan: this rank's ShardPlan when `weights` are shards (device.init_comm must have been called)."""
+        self.device, self.conf, self.weights, self.plan = device, conf, weights, plan          # keep the tensors alive
         L = conf.n_layers
         cconf = capi.ccr_llama_config(conf.n_heads, conf.n_kv_heads, L, conf.embedding_dim, conf.hidden_dim, conf.seq_len,
-                                      conf.vocab_size, conf.rope_dim or 0, conf.rms_norm_eps, int(f16_kv))
+                                      conf.vocab_size, conf.rope_dim or 0, conf.rms_norm_eps, int(f16_kv),
+                                      plan.rank if plan else 0, plan.world if plan else 1, plan.hidden_local if plan else conf.hidden_dim)
 
         def arr(key):
             a = (C.c_void_p * L)(*[t.buf.handle.value for t in weights[key]])
@@ -94,25 +97,22 @@ class LlamaRunner:
             self.device.lib.ccr_runner_destroy(self.handle)
             self.handle = None
 
-    # algorithmic weight bytes streamed per decoded token: every matmul weight once
+    # algorithmic weight bytes streamed per decoded token: every matmul weight once (THIS rank's shards)
     def weight_bytes_per_token(self):
-        c = self.conf
         w = self.weights
-        kv_dim = c.head_size() * c.n_kv_heads
         total = 0
-        for l in range(c.n_layers):
-            total += weight_bytes(w["wq"][l].dtype(), c.embedding_dim, c.embedding_dim)
-            total += weight_bytes(w["wk"][l].dtype(), kv_dim, c.embedding_dim) + weight_bytes(w["wv"][l].dtype(), kv_dim, c.embedding_dim)
-            total += weight_bytes(w["wo"][l].dtype(), c.embedding_dim, c.embedding_dim)
-            total += weight_bytes(w["ffn_gate"][l].dtype(), c.hidden_dim, c.embedding_dim) + weight_bytes(w["ffn_up"][l].dtype(), c.hidden_dim, c.embedding_dim)
-            total += weight_bytes(w["ffn_down"][l].dtype(), c.embedding_dim, c.hidden_dim)
+        for key in ("wq", "wk", "wv", "wo", "ffn_gate", "ffn_up", "ffn_down"):
+            for t in w[key]:
+                r, c = t.shape()
+                total += weight_bytes(t.dtype(), r, c)
         ow = w.get("output_weight") if w.get("output_weight") is not None else w["token_embed"]
-        total += weight_bytes(ow.dtype(), c.vocab_size, c.embedding_dim)
-        return total
+        r, c = ow.shape()
+        return total + weight_bytes(ow.dtype(), r, c)
 
 
-def load_gguf(path: str, device: CudaTensorDevice):
-    """-> (LlamaConfig, weights dict, tokenizer dict).  Dims are reversed into [rows, cols] (model.rs:474)."""
+def load_gguf(path: str, device: CudaTensorDevice, shard=None, f16_kv=False):
+    """-> (LlamaConfig, weights dict, tokenizer dict).  Dims are reversed into [rows, cols] (model.rs:474).
+    shard = (rank, world): upload only this rank's rows / block columns (sharding.py); the plan is returned as w["plan"]."""
     import gguf
     rd = gguf.GGUFReader(path)
     f = rd.fields
@@ -130,17 +130,29 @@ def load_gguf(path: str, device: CudaTensorDevice):
                        int(scalar(f"{arch}.rope.dimension_count")) if f"{arch}.rope.dimension_count" in f else 0)
     tensors = {t.name: t for t in rd.tensors}
 
-    def load(name):
+    plan = None
+    if shard is not None and shard[1] > 1:
+        plan = sharding.make_plan(conf.n_heads, conf.n_kv_heads, conf.embedding_dim, conf.hidden_dim, conf.vocab_size,
+                                  int(tensors["blk.0.ffn_down.weight"].tensor_type), shard[0], shard[1], f16_kv)
+
+    def load(name, kind=None):
         t = tensors[name]
         shape = [int(d) for d in reversed(t.shape.tolist())]
-        return CudaTensor.from_cpu(np.ascontiguousarray(t.data).view(np.uint8).reshape(-1), shape, int(t.tensor_type), device)
+        data = np.ascontiguousarray(t.data).view(np.uint8).reshape(-1)
+        if plan is not None and kind is not None:
+            data, shape = sharding.shard_bytes(kind, data, shape[0], shape[1], int(t.tensor_type), plan)
+        return CudaTensor.from_cpu(data, shape, int(t.tensor_type), device)
     L = conf.n_layers
     names = {"wq": "attn_q", "wk": "attn_k", "wv": "attn_v", "wo": "attn_output", "ffn_gate": "ffn_gate", "ffn_down": "ffn_down",
              "ffn_up": "ffn_up", "rms_att": "attn_norm", "rms_ffn": "ffn_norm"}
-    w = {k: [load(f"blk.{l}.{v}.weight") for l in range(L)] for k, v in names.items()}
+    w = {k: [load(f"blk.{l}.{v}.weight", k) for l in range(L)] for k, v in names.items()}
     w["token_embed"] = load("token_embd.weight")
     w["rms_final"] = load("output_norm.weight")
-    w["output_weight"] = load("output.weight") if "output.weight" in tensors else None
+    if "output.weight" in tensors:
+        w["output_weight"] = load("output.weight", "output_weight")
+    else:           # tied classifier (llama2.rs:201-206): the sharded path needs its own row shard of token_embd
+        w["output_weight"] = load("token_embd.weight", "output_weight") if plan is not None else None
+    w["plan"] = plan
     tok = {"tokens": tokens, "scores": [float(f["tokenizer.ggml.scores"].parts[i][0]) for i in f["tokenizer.ggml.scores"].data],
            "bos": int(scalar("tokenizer.ggml.bos_token_id")), "eos": int(scalar("tokenizer.ggml.eos_token_id"))}
     return conf, w, tok
@@ -156,15 +168,21 @@ def synth_scale(dtype, k):
 
 
 def synthetic_weights(device: CudaTensorDevice, conf: LlamaConfig, wtype: int, classifier_type: int | None = None,
-                      seed: int = 0x5EED, rows_divisor: int = 1):
-    """Valid, non-degenerate random blocks generated ON the device (never shipped through gpurun)."""
+                      seed: int = 0x5EED, plan: "sharding.ShardPlan | None" = None):
+    """Valid, non-degenerate random blocks generated ON the device (never shipped through gpurun).
+    plan: generate only this rank's shard of every tensor (same bytes as the corresponding slice of the full model)."""
     ct = wtype if classifier_type is None else classifier_type
     dim, hid, kv = conf.embedding_dim, conf.hidden_dim, conf.head_size() * conf.n_kv_heads
     tid = [0]
 
-    def syn(rows, cols, t):
+    def syn(rows, cols, t, kind=None):
         tid[0] += 1
-        return CudaTensor.synth([rows, cols], t, device, seed, tid[0], synth_scale(t, cols))
+        if plan is None or plan.world == 1 or kind not in sharding.CUTS:
+            return CudaTensor.synth([rows, cols], t, device, seed, tid[0], synth_scale(t, cols))
+        how, attr = sharding.CUTS[kind]
+        first, count = getattr(plan, attr)
+        r0, nr, c0, nc = (first, count, 0, cols) if how == "rows" else (0, rows, first, count)
+        return CudaTensor.synth_slice([rows, cols], t, device, seed, tid[0], synth_scale(t, cols), r0, nr, c0, nc)
     rng = np.random.default_rng(seed)
 
     def norm():
@@ -172,11 +190,12 @@ def synthetic_weights(device: CudaTensorDevice, conf: LlamaConfig, wtype: int, c
     L = conf.n_layers
     w = {"wq": [], "wk": [], "wv": [], "wo": [], "ffn_gate": [], "ffn_down": [], "ffn_up": [], "rms_att": [], "rms_ffn": []}
     for _ in range(L):
-        w["wq"].append(syn(dim, dim, wtype)); w["wk"].append(syn(kv, dim, wtype)); w["wv"].append(syn(kv, dim, wtype))
-        w["wo"].append(syn(dim, dim, wtype))
-        w["ffn_gate"].append(syn(hid, dim, wtype)); w["ffn_up"].append(syn(hid, dim, wtype)); w["ffn_down"].append(syn(dim, hid, wtype))
+        w["wq"].append(syn(dim, dim, wtype, "wq")); w["wk"].append(syn(kv, dim, wtype, "wk")); w["wv"].append(syn(kv, dim, wtype, "wv"))
+        w["wo"].append(syn(dim, dim, wtype, "wo"))
+        w["ffn_gate"].append(syn(hid, dim, wtype, "ffn_gate")); w["ffn_up"].append(syn(hid, dim, wtype, "ffn_up"))
+        w["ffn_down"].append(syn(dim, hid, wtype, "ffn_down"))
         w["rms_att"].append(norm()); w["rms_ffn"].append(norm())
     w["token_embed"] = syn(conf.vocab_size, dim, wtype)
-    w["output_weight"] = syn(conf.vocab_size, dim, ct)
+    w["output_weight"] = syn(conf.vocab_size, dim, ct, "output_weight")
     w["rms_final"] = norm()
     return w

@@ -89,6 +89,26 @@ class CudaTensorDevice:
 
     def synchronize(self): self.check(self.lib.cc_device_synchronize(self.handle))
 
+    # ---- sharded path: exchange window of this rank (comm.cu).  `exchange(bytes) -> [bytes of every rank]` is any
+    # all-gather of small host blobs (torch.distributed.all_gather_object in bench.py / the tests) ----------------------------
+    def init_comm(self, rank, world, exchange=None, transport="p2p"):
+        handle = (C.c_uint8 * 64)()
+        self.check(self.lib.cc_comm_create(self.handle, rank, world, handle))
+        if world > 1 and exchange is None:
+            raise CudaError("init_comm: an exchange function is required for world > 1")
+        blobs = exchange(bytes(handle)) if world > 1 else [bytes(handle)]
+        allh = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(blobs))
+        self.check(self.lib.cc_comm_connect(self.handle, allh))
+        if transport == "nccl":
+            uid = (C.c_uint8 * 128)()
+            if rank == 0:
+                self.check(self.lib.cc_comm_nccl_unique_id(self.handle, uid))
+            uid0 = exchange(bytes(uid))[0] if world > 1 else bytes(uid)
+            self.check(self.lib.cc_comm_init_nccl(self.handle, (C.c_uint8 * 128).from_buffer_copy(uid0)))
+        elif transport != "p2p":
+            raise CudaError(f"unknown transport {transport}")
+        self.rank, self.world = rank, world
+
     def timer_begin(self): self.check(self.lib.cc_bench_timer_begin(self.handle))
 
     def timer_end(self) -> float:
@@ -190,6 +210,14 @@ class CudaTensor:
         device.check(device.lib.cc_tensor_synth(device.handle, _shape_arr(shape), len(shape), dtype, seed, tensor_id, scale, C.byref(h)))
         return cls(_Buf(device, h), TensorStrider(shape), device)
 
+    @classmethod
+    def synth_slice(cls, shape, dtype, device, seed, tensor_id, scale, row0, nrows, col0, ncols):
+        """rows [row0, +nrows) x columns [col0, +ncols) of the tensor `synth` would generate (sharded path)."""
+        h = C.c_void_p()
+        device.check(device.lib.cc_tensor_synth_slice(device.handle, _shape_arr(shape), len(shape), dtype, seed, tensor_id, scale,
+                                                      row0, nrows, col0, ncols, C.byref(h)))
+        return cls(_Buf(device, h), TensorStrider([nrows, ncols]), device)
+
     # -- metadata (host side) ------------------------------------------------------------------------------
     def dtype(self): return int(self.device.lib.cc_tensor_dtype(self.buf.handle))
     def shape(self): return list(self._strider.shape)
@@ -263,6 +291,13 @@ class CudaTensor:
     def mul_inplace(self, rhs): return self._inplace(self.device.lib.cc_mul_inplace, C.byref(rhs._view()))
     def add_inplace(self, rhs): return self._inplace(self.device.lib.cc_add_inplace, C.byref(rhs._view()))
     def scale_inplace(self, rhs): return self._inplace(self.device.lib.cc_scale_inplace, float(rhs))
+
+    # -- exchange step of the sharded path (crabml_cuda.h; not part of the reference's trait) ------------------
+    def all_reduce_sum_inplace(self): return self._inplace(self.device.lib.cc_all_reduce_sum_inplace)
+
+    def all_gather_from(self, piece):
+        self.device.check(self.device.lib.cc_all_gather(self.device.handle, C.byref(self._view()), C.byref(piece._view())))
+        return self
 
     # -- hot path ----------------------------------------------------------------------------------------------------
     def matmul_vec(self, x):

@@ -145,6 +145,28 @@ CC_API int cc_dump_debug_tensor(cc_device* dev, const char* name, float* dst, si
 /* quantize an F32 vector exactly as matmul_vec does internally and return the reference-layout
  * activation blocks (Q8_0 / Q8_1 / Q8_K bytes) to the host: parity tests of a3-a5. */
 CC_API int cc_test_quantize_activation(cc_device* dev, const cc_view* x, int32_t act_type, void* dst, size_t nbytes);
+/* ---- sharded decode: the exchange step ---------------------------------------------------------
+ * The reference is single-device; its unit of parallelism is the output row (matmul_vec.rs:41-76 splits rows over
+ * the thread pool).  Across GPUs the same split leaves two exchanges per layer: a sum of [dim] partials after the
+ * column-split `wo` and `ffn_down`, and a gather of the row-split classifier's logit slices.
+ * One process per GPU.  cc_comm_create allocates this rank's exchange window and returns its 64-byte CUDA IPC handle;
+ * the caller distributes the handles (torch.distributed / any side channel) and passes all of them to
+ * cc_comm_connect.  cc_comm_init_nccl switches the transport to NCCL (baseline; id from cc_comm_nccl_unique_id on rank 0). */
+CC_API int cc_comm_create(cc_device* dev, int32_t rank, int32_t world, uint8_t* handle_out_64);
+CC_API int cc_comm_connect(cc_device* dev, const uint8_t* handles_world_x_64);
+CC_API int cc_comm_nccl_unique_id(cc_device* dev, uint8_t* id_out_128);
+CC_API int cc_comm_init_nccl(cc_device* dev, const uint8_t* id_128);
+CC_API int32_t cc_comm_rank(cc_device* dev);
+CC_API int32_t cc_comm_world_size(cc_device* dev);
+/* x (contiguous f32, <= 32768 elements, multiple of 4) = sum over ranks of x, same bits on every rank */
+CC_API int cc_all_reduce_sum_inplace(cc_device* dev, const cc_view* x);
+/* dst[r * n + i] = src of rank r [i]; src: n contiguous f32 (same n on every rank), dst: world * n */
+CC_API int cc_all_gather(cc_device* dev, const cc_view* dst, const cc_view* src);
+/* synthetic shard: rows [row0, row0+nrows) x columns [col0, col0+ncols) of the tensor cc_tensor_synth would make */
+CC_API int cc_tensor_synth_slice(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t ggml_type, uint64_t seed,
+                                 uint64_t tensor_id, float scale, int64_t row0, int64_t nrows, int64_t col0,
+                                 int64_t ncols, cc_buf** out);
+
 /* synthetic weights generated on device in the device layout: counter-based
  * RNG, identical bytes to tests/synth.py's CPU generator for the same (seed, tensor_id). */
 CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t ggml_type,

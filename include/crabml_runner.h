@@ -22,6 +22,9 @@ typedef struct ccr_llama_config {
     int32_t rope_dim;          /* <= 0: use head_dim (llama2.rs:218) */
     float rms_norm_eps;
     int32_t use_f16_kv_cache;  /* llama2.rs:51-55 */
+    /* sharded decode (not in the reference: SURVEY 8e).  shard_world <= 1: single device.  Otherwise the weights passed to
+     * ccr_runner_create are THIS rank's shards (crabml_b200/sharding.py) and hidden_local is its share of hidden_dim. */
+    int32_t shard_rank, shard_world, hidden_local;
 } ccr_llama_config;
 
 /* LlamaWeights<T>, model.rs:55-84; arrays have n_layers entries; output_weight may be NULL (llama2.rs:201-206) */

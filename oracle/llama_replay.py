@@ -174,12 +174,15 @@ def sample_argmax(logits) -> int:        # sampler.rs:109-116: Iterator::max_by 
 class Llama2Runner:
     """llama2.rs:26-211 generic over the tensor class T (T.alloc / T.from_cpu are classmethods)."""
 
-    def __init__(self, T, conf: LlamaConfig, weights: LlamaWeights, device, seq_len, use_f16_kv_cache=False):
-        self.T, self.conf, self.weights, self.device = T, conf, weights, device
+    def __init__(self, T, conf: LlamaConfig, weights: LlamaWeights, device, seq_len, use_f16_kv_cache=False, world=1):
+        """world > 1: `weights` are one rank's shards (crabml_b200/sharding.py) and T has all_reduce_sum_inplace /
+        all_gather_from -- the same replay the C++ host runs in sharded mode (llama2_runner.cpp)."""
+        self.T, self.conf, self.weights, self.device, self.world = T, conf, weights, device, world
         kv_dtype = F16 if use_f16_kv_cache else F32
         self.logits = np.zeros(conf.vocab_size, np.float32)
-        self.key_cache = [T.alloc([conf.n_kv_heads, seq_len, conf.head_size()], kv_dtype, device).resize(1, 0) for _ in range(conf.n_layers)]
-        self.value_cache = [T.alloc([conf.n_kv_heads, seq_len, conf.head_size()], kv_dtype, device).resize(1, 0) for _ in range(conf.n_layers)]
+        nkv = conf.n_kv_heads // world
+        self.key_cache = [T.alloc([nkv, seq_len, conf.head_size()], kv_dtype, device).resize(1, 0) for _ in range(conf.n_layers)]
+        self.value_cache = [T.alloc([nkv, seq_len, conf.head_size()], kv_dtype, device).resize(1, 0) for _ in range(conf.n_layers)]
 
     def kv_cache_len(self):
         return self.key_cache[0].shape()[1]
@@ -213,12 +216,14 @@ class Llama2Runner:
         x_final.copy_rows_from(x, [len(tokens) - 1])
         output_weight = self.weights.output_weight if self.weights.output_weight is not None else self.weights.token_embed
         logits = output_weight.matmul_vec(x_final)
+        if self.world > 1:
+            logits = T.alloc([self.conf.vocab_size], F32, self.device).all_gather_from(logits)
         self.logits = np.asarray(logits.export(), np.float32)
         return self.logits
 
     def forward_llama(self, tokens, pos):        # llama2.rs:213-281
         T, conf, w = self.T, self.conf, self.weights
-        embed_dim, n_heads, n_kv_heads = conf.embedding_dim, conf.n_heads, conf.n_kv_heads
+        embed_dim, n_heads, n_kv_heads = conf.embedding_dim, conf.n_heads // self.world, conf.n_kv_heads // self.world
         head_dim = conf.head_size()
         rope_dim = conf.rope_dim if conf.rope_dim is not None else head_dim
         n_batch = len(tokens)
@@ -242,7 +247,9 @@ class Llama2Runner:
             q = q.rope_inplace(ROPE_LLAMA, pos, rope_dim)
             k = k.rope_inplace(ROPE_LLAMA, pos, rope_dim)
 
-            x = self.forward_multi_query_attention(q, k, v, l, pos, n_kv_heads, n_heads, embed_dim, head_dim, n_batch)
+            x = self.forward_multi_query_attention(q, k, v, l, pos, n_kv_heads, n_heads, n_heads * head_dim, head_dim, n_batch)
+            if self.world > 1:
+                x = x.all_reduce_sum_inplace()
             x = x.with_name(f"attn_out:{l}:{pos}")
             x = x.add_inplace(x_attn_orig)
             x = self.forward_ffn(x, l, pos)
@@ -289,6 +296,8 @@ class Llama2Runner:
         h1 = h1.silu_inplace()
         h1 = h1.mul_inplace(h2)
         x = w.ffn_down_weight[l].matmul_vec(h1)
+        if self.world > 1:
+            x = x.all_reduce_sum_inplace()
         x = x.add_inplace(x_orig_ffn)
         return x
 

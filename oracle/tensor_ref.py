@@ -253,6 +253,17 @@ class OracleTensor:
     def mul_inplace(self, rhs): return self._binary(rhs, oc.mul_)
     def add_inplace(self, rhs): return self._binary(rhs, oc.add_)
 
+    # -- exchange step of the sharded replay (the reference has none; device.comm = object with all_reduce / all_gather
+    #    over numpy arrays, e.g. torch.distributed gloo in tests/test_sharded_gloo.py) ------------------------------------
+    def all_reduce_sum_inplace(self):
+        a = self._f32_owned()
+        a[:self._strider.len()] = self.device.comm.all_reduce(a[:self._strider.len()])
+        return self
+
+    def all_gather_from(self, piece):
+        self._f32_owned()[:self._strider.len()] = self.device.comm.all_gather(piece.buf[:piece._strider.len()])
+        return self
+
     def scale_inplace(self, rhs):                            # cpu_tensor.rs:404-410
         return self._binary(OracleTensor.new([rhs], [1], self.device), oc.mul_)
 

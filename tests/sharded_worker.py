@@ -1,0 +1,191 @@
+"""Worker of the multi-process tests of the sharded decode path.  Launched by tests/test_sharded_gloo.py
+(CPU, gloo, oracle tensors: validates the shard plan + replay) and tests/test_gpu_sharded.py (one process per GPU: the
+product path -- p2p one-shot exchange in eager mode, in the CUDA-graph mode and inside the megakernel, and the NCCL
+baseline) under `python -m torch.distributed.run --nproc-per-node N tests/sharded_worker.py --mode cpu|gpu`.
+Exit code 0 = every check passed on every rank."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.distributed as dist
+
+from crabml_b200 import sharding
+from oracle import oracle as oc
+from oracle.llama_replay import Llama2Runner, LlamaConfig as OConf, LlamaWeights
+from oracle.synth import synth_weight
+from oracle.tensor_ref import OracleDevice, OracleTensor
+
+SEED = 0xC0FFEE
+KINDS = {"wq": 1, "wk": 2, "wv": 3, "wo": 4, "ffn_gate": 5, "ffn_up": 6, "ffn_down": 7}
+
+
+class GlooComm:
+    """all_reduce / all_gather of numpy f32 rows over torch.distributed (CPU tensors -> gloo)."""
+
+    def all_reduce(self, a):
+        world = dist.get_world_size()
+        parts = [torch.empty(a.size, dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(a, np.float32)))
+        out = parts[0].numpy().copy()
+        for p in parts[1:]:                      # rank order, like the device kernel (comm.cu)
+            out = out + p.numpy()
+        return out
+
+    def all_gather(self, a):
+        world = dist.get_world_size()
+        parts = [torch.empty(a.size, dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(a, np.float32)))
+        return np.concatenate([p.numpy() for p in parts])
+
+
+def synth_scale(t, k):
+    from crabml_b200.runner import synth_scale as s
+    return s(t, k)
+
+
+def oracle_model(conf, wt, ct, plan, device):
+    """Oracle weights of the full model (plan None) or of one rank's shard, from the same synthetic bytes."""
+    dim, hid, hd = conf.embedding_dim, conf.hidden_dim, conf.embedding_dim // conf.n_heads
+    kv = hd * conf.n_kv_heads
+
+    def make(kind, rows, cols, t, tid):
+        raw = synth_weight(t, rows, cols, SEED, tid, synth_scale(t, cols))
+        shape = [rows, cols]
+        if plan is not None:
+            raw, shape = sharding.shard_bytes(kind, raw, rows, cols, t, plan)
+        return OracleTensor.from_cpu(raw, shape, t, device)
+    rng = np.random.default_rng(SEED)
+
+    def norm():
+        return OracleTensor.from_cpu((1.0 + 0.05 * rng.standard_normal(dim)).astype(np.float32), [dim], oc.F32, device)
+    L = conf.n_layers
+    per = {k: [] for k in KINDS}
+    ra, rf = [], []
+    for l in range(L):
+        base = 16 * (l + 1)
+        per["wq"].append(make("wq", dim, dim, wt, base + 1)); per["wk"].append(make("wk", kv, dim, wt, base + 2))
+        per["wv"].append(make("wv", kv, dim, wt, base + 3)); per["wo"].append(make("wo", dim, dim, wt, base + 4))
+        per["ffn_gate"].append(make("ffn_gate", hid, dim, wt, base + 5)); per["ffn_up"].append(make("ffn_up", hid, dim, wt, base + 6))
+        per["ffn_down"].append(make("ffn_down", dim, hid, wt, base + 7))
+        ra.append(norm()); rf.append(norm())
+    return LlamaWeights(token_embed=make("token_embed", conf.vocab_size, dim, wt, 8), wq=per["wq"], wk=per["wk"], wv=per["wv"], wo=per["wo"],
+                        ffn_gate_weight=per["ffn_gate"], ffn_down_weight=per["ffn_down"], ffn_up_weight=per["ffn_up"], rms_att_weight=ra,
+                        rms_ffn_weight=rf, rms_final_weight=norm(), output_weight=make("output_weight", conf.vocab_size, dim, ct, 9))
+
+
+def run_cpu(rank, world):
+    conf = OConf(4, 4, 2, 128, 256, 64, 512, 1e-5, 32)
+    tokens = [1, 77, 300, 5]
+    for wt, ct in ((oc.Q8_0, oc.Q8_0), (oc.Q4_0, oc.Q8_0)):
+        plan = sharding.make_plan(conf.n_heads, conf.n_kv_heads, conf.embedding_dim, conf.hidden_dim, conf.vocab_size, wt, rank, world)
+        dev = OracleDevice()
+        dev.comm = GlooComm()
+        rs = Llama2Runner(OracleTensor, conf, oracle_model(conf, wt, ct, plan, dev), dev, 16, world=world)
+        got = [rs.forward([t], p).copy() for p, t in enumerate(tokens)]
+        # every rank holds the same logits, bit for bit (rank-ordered sums)
+        for g in got:
+            ref = torch.from_numpy(g.copy())
+            dist.broadcast(ref, 0)
+            assert np.array_equal(ref.numpy().view(np.uint32), g.view(np.uint32)), "ranks diverged"
+        if rank == 0:
+            full = Llama2Runner(OracleTensor, conf, oracle_model(conf, wt, ct, None, OracleDevice()), OracleDevice(), 16)
+            for p, t in enumerate(tokens):
+                want = full.forward([t], p)
+                rel = float(np.abs(got[p] - want).max() / np.abs(want).max())
+                assert rel < 3e-2, (oc.TYPE_NAMES[wt], p, rel)       # only the f32 grouping of the two partial sums differs
+                assert np.argmax(got[p]) == np.argmax(want) or rel < 1e-3
+    return 0
+
+
+def run_gpu(rank, world, transports):
+    from crabml_b200 import CudaTensor, CudaTensorDevice, capi
+    from crabml_b200 import runner as R
+    torch.cuda.set_device(rank)
+
+    def exchange(blob):
+        out = [None] * world
+        dist.all_gather_object(out, blob)
+        return out
+    # ---- 1. the two exchange ops, eager: bit-exact against a rank-ordered numpy sum ------------------------------------
+    for transport in transports:
+        dev = CudaTensorDevice(rank)
+        dev.init_comm(rank, world, exchange, transport)
+        for n in (4096, 32, 32768):
+            for rep in range(3):
+                rng = np.random.default_rng(1000 * rep + n)
+                parts = [rng.standard_normal(n).astype(np.float32) for _ in range(world)]
+                x = CudaTensor.new(parts[rank], [n], dev).all_reduce_sum_inplace()
+                want = parts[0].copy()
+                for p in parts[1:]:
+                    want = want + p
+                got = x.export()
+                if transport == "p2p":
+                    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (transport, n, rep)
+                else:
+                    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+                full = CudaTensor.alloc([n * world], capi.F32, dev).all_gather_from(CudaTensor.new(parts[rank], [n], dev))
+                assert np.array_equal(full.export(), np.concatenate(parts)), (transport, n, rep)
+        dist.barrier()
+        dev.close()
+    # ---- 2. Llama-2-7B-shaped model (2 layers), synthetic shards: every mode vs the single-GPU logits --------------------
+    conf = R.LlamaConfig(32, 32, 2, 4096, 11008, 4096, 32000, 1e-5, 128)
+    tokens = [1, 777, 31999, 5, 6, 7]
+    want = None
+    if rank == 0:
+        dev = CudaTensorDevice(rank, lazy=0)
+        w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=7)
+        r = R.LlamaRunner(dev, conf, w, 16)
+        want = np.stack([r.forward([t], p).copy() for p, t in enumerate(tokens)])
+        r.close(); del w; dev.close()
+    plan = sharding.make_plan(conf.n_heads, conf.n_kv_heads, conf.embedding_dim, conf.hidden_dim, conf.vocab_size, capi.Q8_0, rank, world)
+    results = {}
+    for transport, lazy in [(t, l) for t in transports for l in ((0, 1, 2) if t == "p2p" else (0, 1))]:
+        dev = CudaTensorDevice(rank, lazy=lazy)
+        dev.init_comm(rank, world, exchange, transport)
+        w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=7, plan=plan)
+        r = R.LlamaRunner(dev, conf, w, 16, plan=plan)
+        got = np.stack([r.forward([t], p).copy() for p, t in enumerate(tokens)])
+        assert np.isfinite(got).all()
+        ref = torch.from_numpy(got.copy()).cuda()
+        dist.broadcast(ref, 0)
+        if transport == "p2p":
+            assert np.array_equal(ref.cpu().numpy().view(np.uint32), got.view(np.uint32)), ("ranks diverged", transport, lazy)
+        if lazy:
+            st = dev.lazy_stats()
+            assert st["uncached"] == 0 and st["graph_replays"] >= 2, st
+        if rank == 0:
+            rel = float(np.abs(got - want).max() / np.abs(want).max())
+            assert rel < 3e-2, (transport, lazy, rel)
+            results[(transport, lazy)] = rel
+        dist.barrier()
+        r.close(); del w; dev.close()
+    if rank == 0:
+        print("sharded parity vs single GPU (max rel):", results, flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", choices=["cpu", "gpu"], required=True)
+    ap.add_argument("--transports", default="p2p,nccl")
+    a = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if a.mode == "cpu":
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        rc = run_cpu(rank, world)
+    else:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+        rc = run_gpu(rank, world, a.transports.split(","))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(rc)
+
+
+if __name__ == "__main__":
+    main()
