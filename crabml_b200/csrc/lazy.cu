@@ -415,6 +415,13 @@ struct Fuser {
         if (nq.type != MK_NORMQ || mv.type != MK_MATVEC || nq.write_back || nq.n != mv.mv.k) return;
         mv.x = nq.x; mv.orig = nq.orig; mv.norm_w = nq.norm_w; mv.eps = nq.eps; mv.n = nq.n;
         P.phases.erase(P.phases.begin() + at);
+        // sharded path: the REDUCE phase that produced x folds into the same prologue (x itself is dead after this group:
+        // !write_back), so an exchange costs no phase of its own
+        if (at >= 1 && P.phases[at - 1].type == MK_REDUCE && P.phases[at - 1].red_dst == P.phases[at].x && P.phases[at - 1].red_n == P.phases[at].n) {
+            MkPhase& m2 = P.phases[at];
+            m2.red_n = P.phases[at - 1].red_n; m2.red_res = P.phases[at - 1].red_res;
+            P.phases.erase(P.phases.begin() + (at - 1));
+        }
     }
 
     void run() {

@@ -246,12 +246,28 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         float* s_red = (float*)(smem + (size_t)nbp * 40);                // scratch behind the activation arrays
         float* s_x = s_red + 64;                                          // f32 copy of x, then of the norm weights
         float* s_w = s_x + n;
-        {   // one L2 round trip: every 16-byte chunk of x (and of the norm weights) requested at once with cp.async.cg
+        {   // one L2 round trip: every 16-byte chunk of x (and of the norm weights) requested at once
             const int n4 = n >> 2;
             const unsigned sx = (unsigned)__cvta_generic_to_shared(s_x), sw = (unsigned)__cvta_generic_to_shared(s_w);
-            for (int i = threadIdx.x; i < n4; i += MK_THREADS) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 16), "l"(ph.x + i * 4) : "memory");
-                if (ph.norm_w) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sw + i * 16), "l"(ph.norm_w + i * 4) : "memory");
+            if (ph.norm_w)
+                for (int i = threadIdx.x; i < n4; i += MK_THREADS)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sw + i * 16), "l"(ph.norm_w + i * 4) : "memory");
+            if (ph.red_n) {
+                // second half of the exchange that ended the previous phase (comm.cu): x = sum over ranks of the partial rows
+                // in rank order (+ residual), rebuilt by every CTA from this GPU's window -- no separate REDUCE phase
+                const float* base = comm.data[comm.rank] + (size_t)(xseq & 1u) * CC_COMM_MAX_RANKS * CC_COMM_MAX_ELEMS;
+                for (int i = threadIdx.x; i < n4; i += MK_THREADS) {
+                    float4 acc4 = __ldcg((const float4*)base + i);
+                    for (int p = 1; p < comm.world; p++) {
+                        const float4 t4 = __ldcg((const float4*)(base + (size_t)p * CC_COMM_MAX_ELEMS) + i);
+                        acc4.x += t4.x; acc4.y += t4.y; acc4.z += t4.z; acc4.w += t4.w;
+                    }
+                    if (ph.red_res) { const float4 r4 = __ldcg((const float4*)ph.red_res + i); acc4.x += r4.x; acc4.y += r4.y; acc4.z += r4.z; acc4.w += r4.w; }
+                    ((float4*)s_x)[i] = acc4;
+                }
+            } else {
+                for (int i = threadIdx.x; i < n4; i += MK_THREADS)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 16), "l"(ph.x + i * 4) : "memory");
             }
             asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             __syncthreads();
@@ -270,16 +286,31 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
             rms = sqrtf(t / (float)n + ph.eps);
         }
         if (ph.orig && blockIdx.x == 0)                              // Tensor::dup of the un-normalised row (llama2.rs:227,607)
-            for (int i = threadIdx.x; i < n; i += MK_THREADS) ph.orig[i] = s_x[i];
-        for (int b = warp; b < nbp; b += MK_WARPS) {
-            float xv = b < nb ? s_x[b * 32 + lane] : 0.0f;
-            if (ph.norm_w && b < nb) xv = (xv / rms) * s_w[b * 32 + lane];
-            float amax = warp_max(fabsf(xv));
-            float d = amax / 127.0f;
-            int q = b < nb ? __float2int_rz(xv / d) : 0;
-            s_q[b * 32 + lane] = (int8_t)q;
-            if constexpr (TYPE == CC_Q4_0) { int sq = warp_sum_i(q); if (lane == 0) s_s[b] = sq; }
-            if (lane == 0) s_d[b] = b < nb ? __half2float(__float2half_rn(d)) : 0.0f;
+            for (int i = threadIdx.x; i < (n >> 2); i += MK_THREADS) ((float4*)ph.orig)[i] = ((const float4*)s_x)[i];
+        // quantise: 4 consecutive elements per thread, 8 threads per 32-block, 64 blocks per pass (same arithmetic per element as
+        // quantize.cu: d = amax / 127, q = trunc(x / d), stored scale = f32(f16(d)))
+        const int sub = threadIdx.x & 7;
+        for (int b = threadIdx.x >> 3; b < nbp; b += MK_THREADS / 8) {        // nbp % 128 == 0: uniform trip count per warp
+            const bool live = b < nb;
+            float4 v = live ? ((const float4*)s_x)[b * 8 + sub] : make_float4(0, 0, 0, 0);
+            if (ph.norm_w && live) {
+                const float4 w4 = ((const float4*)s_w)[b * 8 + sub];
+                v.x = (v.x / rms) * w4.x; v.y = (v.y / rms) * w4.y; v.z = (v.z / rms) * w4.z; v.w = (v.w / rms) * w4.w;
+            }
+            float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            const float d = amax / 127.0f;
+            const int q0 = live ? __float2int_rz(v.x / d) : 0, q1 = live ? __float2int_rz(v.y / d) : 0;
+            const int q2 = live ? __float2int_rz(v.z / d) : 0, q3 = live ? __float2int_rz(v.w / d) : 0;
+            ((int*)s_q)[b * 8 + sub] = (q0 & 255) | ((q1 & 255) << 8) | ((q2 & 255) << 16) | (q3 << 24);
+            if constexpr (TYPE == CC_Q4_0) {
+                int sq = q0 + q1 + q2 + q3;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (sub == 0) s_s[b] = sq;
+            }
+            if (sub == 0) s_d[b] = live ? __half2float(__float2half_rn(d)) : 0.0f;
         }
     } else {   // stage the quantised activation (written by other CTAs in the previous phase: L2 loads)
         const uint8_t* act = (const uint8_t*)A.act;
