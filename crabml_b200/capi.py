@@ -65,13 +65,16 @@ def load_library(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
+    alt = os.environ.get("CRABML_CUDA_LIB")          # developer A/B: another build of the same library
+    if alt:
+        build_if_missing = False
     if build_if_missing:
         from . import build as _build
         if _build.needs_build():
             _build.build()
     if not os.path.exists(LIB_PATH):
         raise CudaError(f"{LIB_PATH} is missing: run `python -m crabml_b200.build` (no CPU fallback exists)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(alt if alt else LIB_PATH)
     vp, i32, i64, u64, sz, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t, C.c_float
     pv = C.POINTER(cc_view)
     pp = C.POINTER(C.c_void_p)

@@ -232,7 +232,7 @@ struct MkPhase {
     unsigned long long dyn_off, rope_off;   // ATTN {pos, kv_len} / ROWS row list ; RoPE table
     DeqPlanes planes; int src_dtype, dst_dtype, n_rows, pad; long long cols; void* dst;   // ROWS
 };
-size_t cc_mega_smem_for_matvec(int type, int k);
+size_t cc_mega_smem_for_phase(const MkPhase& ph);
 const CommDev* cc_comm_dev(cc_device* dev);
 bool cc_comm_is_nccl(cc_device* dev);
 int cc_comm_world(cc_device* dev);

@@ -76,7 +76,7 @@ LazyState* cc_lazy_create(cc_device* dev) {
     for (int i = 0; i < 2; i++)
         if (cudaMallocHost(&lz->dyn_host[i], lz->dyn_cap) != cudaSuccess || cudaEventCreateWithFlags(&lz->dyn_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete lz; return nullptr; }
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
-    if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 4096);
+    if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 4 * 4096);
     if (cudaMalloc(&lz->bar_dev, 4096) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 4096) != cudaSuccess) { delete lz; return nullptr; }
     return lz;
 }
@@ -311,7 +311,7 @@ struct Fuser {
         for (size_t t = 0; t < n; t++) { P.SP(A.mats.qs[t]); P.SP(A.mats.out[t]); P.S(A.mats.m[t]); }
         P.steps.push_back([=](uint8_t*) { return cc_launch_matvec_stream(d, wt, A); });
         { MkPhase ph = {}; ph.type = MK_MATVEC; ph.wtype = wt; ph.mv = A; if (xchg) { ph.mv.epilogue = 3; ph.xgpu = 1; }
-          P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_matvec(wt, (int)k)); }
+          P.phases.push_back(ph); }
         if (xchg) {
             const int64_t mrows = m0.a.shape[0];
             float* part = A.mats.out[0];
@@ -382,7 +382,7 @@ struct Fuser {
             return cc_launch_attn_decode(d, B);
         });
         { MkPhase ph = {}; ph.type = MK_ATTN; ph.at = A; ph.dyn_off = dyn_off; ph.rope_off = roff; ph.act = cc_act_q8_0(lz->act[1], n_heads * hd);
-          P.phases.push_back(ph); P.mega_smem = std::max(P.mega_smem, (size_t)(3 * hd + ((A.max_len + 8 + 3) & ~3) + 2 * 64 * hd) * 4 + 64); }
+          P.phases.push_back(ph); }
         *obuf = b2.out;
         for (size_t t = i; t < i + 9; t++) q[t].done = true;
         return 9;
@@ -518,6 +518,7 @@ int cc_lazy_flush(cc_device* dev) {
             if (use_mega) {       // phase table lives in device memory for the lifetime of the graph
                 int nxt = -1;
                 for (int t = (int)P.phases.size() - 1; t >= 0; t--) { P.phases[t].next_matvec = nxt; if (P.phases[t].type == MK_MATVEC) nxt = t; }
+                for (auto& ph : P.phases) P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_phase(ph));
                 if (cudaMalloc(&ge.phases_dev, P.phases.size() * sizeof(MkPhase)) != cudaSuccess ||
                     cudaMemcpy(ge.phases_dev, P.phases.data(), P.phases.size() * sizeof(MkPhase), cudaMemcpyHostToDevice) != cudaSuccess)
                     rc = cc_fail(dev, CC_ERR_CUDA, "lazy: phase table upload failed");
@@ -571,8 +572,8 @@ extern "C" CC_API int cc_lazy_mega_profile(cc_device* dev, unsigned long long* t
     if (!dev || !dev->lz || !dev->lz->prof_dev || !ts || !types || !n_out) return CC_ERR_ARG;
     cudaStreamSynchronize(dev->stream);
     int n = (int)dev->lz->prof_types.size();
-    if (n + 1 > cap) return CC_ERR_ARG;
-    if (cudaMemcpy(ts, dev->lz->prof_dev, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return CC_ERR_CUDA;
+    if ((n + 1) * 4 > cap) return CC_ERR_ARG;          // 4 stamps per phase: start, activation ready, rows done, arrived
+    if (cudaMemcpy(ts, dev->lz->prof_dev, (size_t)(n + 1) * 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return CC_ERR_CUDA;
     for (int i = 0; i < n; i++) types[i] = dev->lz->prof_types[i];
     *n_out = n;
     return CC_OK;

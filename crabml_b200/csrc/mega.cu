@@ -68,6 +68,12 @@ __device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblock
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
 
 // ---- NORMQ phase (fused.cu normq_kernel, grid-wide) -----------------------------------------------------------------
@@ -170,6 +176,69 @@ __device__ __forceinline__ float mk_seg_dot(const MkSeg& S, int seg, const int4*
     return acc;
 }
 
+// ---- TMA-staged segments: two more segments per warp wait in shared memory ----------------------------------------------------
+// A segment of a row is ONE contiguous run of bytes in the quant plane (MK_SEG groups x 1 KB for Q8_0, 512 B for Q4_0), so it
+// is fetched with a single cp.async.bulk (TMA, no registers, no LSU instructions) that signals a per-(warp, stage) mbarrier.
+// Together with the two register-resident segments a warp keeps 4 segments = 17 KB in flight, 41 MB per GPU: enough to cover
+// the grid barrier AND the activation prologue of the next phase with streaming.
+#define MK_STAGES 2
+#ifndef MK_DEEP
+#define MK_DEEP 0
+#endif
+#define MK_STAGE_BYTES 4096
+#define MK_STAGING (MK_WARPS * MK_STAGES * MK_STAGE_BYTES)     // 128 KB at the bottom of dynamic shared memory
+struct MkPipe {
+    MkSeg buf0, buf1;                    // register stages (segments u % 4 == 0, 1)
+    uint16_t sc0[MK_SEG], sc1[MK_SEG];   // f16 scales of the two TMA stages (segments u % 4 == 2, 3)
+    unsigned par;                        // bit s = parity the next wait on stage s must see
+};
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nMK_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra MK_WAIT_%=;\n}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+template <int TYPE>
+__device__ __forceinline__ void mk_stage_issue(unsigned stage_smem, unsigned mbar, uint16_t (&sc)[MK_SEG], const MkRowPtr& p, int seg, int nb, int lane, bool valid) {
+    constexpr int GB = TYPE == CC_Q8_0 ? 1024 : 512;
+    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
+    if (valid && lane == 0) {
+        const unsigned off = (unsigned)seg * (MK_SEG * GB);
+        unsigned bytes = (unsigned)nb * BB - off;
+        if (bytes > MK_SEG * GB) bytes = MK_SEG * GB;
+        const uint8_t* src = p.q + off;                    // lane 0: p.q is the row base
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+    }
+    const uint16_t* d = p.d + seg * (MK_SEG * 32);
+#pragma unroll
+    for (int g = 0; g < MK_SEG; g++) sc[g] = valid && ((seg * MK_SEG + g) * 32 + lane < nb) ? d[g * 32] : (uint16_t)0;
+}
+// lanes beyond the row (or groups beyond it) carry scale 0, so whatever bytes the stage holds there contribute exactly 0
+template <int TYPE>
+__device__ __forceinline__ float mk_stage_dot(const int4* st, const uint16_t (&sc)[MK_SEG], int seg, int GR, int last_half_off, int lane, const int4* aq_l, const float* ad_l, const int* as_l) {
+    float acc = 0.0f;
+    const int4* aq = aq_l + seg * (MK_SEG * 64);
+    const float* ad = ad_l + seg * (MK_SEG * 32);
+#pragma unroll
+    for (int g = 0; g < MK_SEG; g++) {
+        if constexpr (TYPE == CC_Q8_0) {
+            const int hoff = (seg * MK_SEG + g == GR - 1 ? last_half_off : 512) >> 4;
+            const int4 wa = st[g * 64 + lane], wb = st[g * 64 + hoff + lane];
+            int sumi = mk_dp16(wa, aq[g * 64]) + mk_dp16(wb, aq[g * 64 + 1]);
+            acc += (float)sumi * h2f_bits(sc[g]) * ad[g * 32];
+        } else {
+            const int4 w = st[g * 32 + lane];
+            int4 lo = make_int4(w.x & 0x0F0F0F0F, w.y & 0x0F0F0F0F, w.z & 0x0F0F0F0F, w.w & 0x0F0F0F0F);
+            int4 hi = make_int4((w.x >> 4) & 0x0F0F0F0F, (w.y >> 4) & 0x0F0F0F0F, (w.z >> 4) & 0x0F0F0F0F, (w.w >> 4) & 0x0F0F0F0F);
+            int sumi = mk_dp16(lo, aq[g * 64]) + mk_dp16(hi, aq[g * 64 + 1]) - 8 * as_l[(seg * MK_SEG + g) * 32];
+            acc += (float)sumi * h2f_bits(sc[g]) * ad[g * 32];
+        }
+    }
+    return acc;
+}
+
 // geometry of one MATVEC phase for this warp
 struct MkGeo {
     int nb, GR, NSEG, U, last_half_off, gw, TW;
@@ -205,21 +274,27 @@ __device__ __forceinline__ MkRowPtr mk_vrow_ptr(const StreamMats& M, const MkGeo
     return p;
 }
 
-// Issue the loads of this warp's first two segments of a MATVEC phase.  Weights are immutable, so this may run
+// Issue the loads of this warp's first two (deep: four) segments of a MATVEC phase.  Weights are immutable, so this may run
 // long before the phase itself -- across barriers and small phases -- keeping HBM busy while the grid synchronises.
 template <int TYPE>
-__device__ __forceinline__ void matvec_prefetch(const StreamArgs& A, MkSeg& buf0, MkSeg& buf1) {
+__device__ __forceinline__ void matvec_prefetch(const StreamArgs& A, MkPipe& P, bool deep, unsigned stage0_smem, unsigned mbar0) {
     const int lane = threadIdx.x & 31;
     const MkGeo g = mk_geo(A);
-    MkRowPtr p0 = mk_vrow_ptr<TYPE>(A.mats, g, 0, lane);
-    mk_seg_load<TYPE>(buf0, p0, 0, g.nb, g.GR, g.last_half_off, lane, g.U > 0);
-    if (g.NSEG > 1) mk_seg_load<TYPE>(buf1, p0, 1, g.nb, g.GR, g.last_half_off, lane, g.U > 1);
-    else { MkRowPtr p1 = mk_vrow_ptr<TYPE>(A.mats, g, 1, lane); mk_seg_load<TYPE>(buf1, p1, 0, g.nb, g.GR, g.last_half_off, lane, g.U > 1); }
+    int l_i = 0, l_seg = 0;
+    MkRowPtr l_ptr = mk_vrow_ptr<TYPE>(A.mats, g, 0, lane);
+    auto advance_load = [&]() { if (++l_seg == g.NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(A.mats, g, ++l_i, lane); } };
+    mk_seg_load<TYPE>(P.buf0, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 0); advance_load();
+    mk_seg_load<TYPE>(P.buf1, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 1); advance_load();
+    if (deep) {
+        mk_stage_issue<TYPE>(stage0_smem, mbar0, P.sc0, l_ptr, l_seg, g.nb, lane, g.U > 2); advance_load();
+        mk_stage_issue<TYPE>(stage0_smem + MK_STAGE_BYTES, mbar0 + 8, P.sc1, l_ptr, l_seg, g.nb, lane, g.U > 3);
+    }
 }
 
-// precondition: buf0 / buf1 hold this warp's segments 0 / 1 (matvec_prefetch)
+// precondition: the pipe holds this warp's segments 0, 1 (registers) and, in deep mode, 2, 3 (TMA stages): matvec_prefetch
 template <int TYPE>
-__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut, MkSeg& buf0, MkSeg& buf1, const CommDev& comm, unsigned xseq) {
+__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut, MkPipe& P, bool deep, const int4* stage0, unsigned stage0_smem, unsigned mbar0,
+                             const CommDev& comm, unsigned xseq, unsigned long long* stamp1) {
     const StreamArgs& A = ph.mv;
     const int k = A.k;
     const MkGeo g = mk_geo(A);
@@ -237,6 +312,9 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
     auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); } };
     advance_load();
     advance_load();
+    if (deep) { advance_load(); advance_load(); }
+    MkSeg& buf0 = P.buf0;
+    MkSeg& buf1 = P.buf1;
     if (ph.x) {
         // Fused prologue: [rms_norm * w] + Q8_0 quantisation of x, computed by EVERY CTA straight into its shared memory
         // (redundant across SMs, ~1.5 us of issue time) -- cheaper than a separate NORMQ phase, which costs a grid barrier
@@ -325,6 +403,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         }
     }
     __syncthreads();
+    if (stamp1) *stamp1 = globaltimer_ns();
     const int4* aq_l = (const int4*)s_q + 2 * lane;
     const float* ad_l = s_d + lane;
     const int* as_l = s_s + lane;
@@ -358,15 +437,44 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
             o[rr] = r;
         }
     };
-    for (int u = 0; u < U; u += 2) {          // two segments (8 KB of Q8_0) in flight per warp at all times
+    if (!deep) {
+        for (int u = 0; u < U; u += 2) {          // two segments (8 KB of Q8_0) in flight per warp at all times
+            acc += mk_seg_dot<TYPE>(buf0, c_seg, aq_l, ad_l, as_l);
+            finish_segment();
+            mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 2 < U);
+            advance_load();
+            if (u + 1 >= U) break;
+            acc += mk_seg_dot<TYPE>(buf1, c_seg, aq_l, ad_l, as_l);
+            finish_segment();
+            mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 3 < U);
+            advance_load();
+        }
+        return;
+    }
+    // deep: four segments in flight per warp, slots rotate register 0, register 1, TMA stage 0, TMA stage 1
+    for (int u = 0; u < U; u += 4) {
         acc += mk_seg_dot<TYPE>(buf0, c_seg, aq_l, ad_l, as_l);
         finish_segment();
-        mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 2 < U);
+        mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 4 < U);
         advance_load();
         if (u + 1 >= U) break;
         acc += mk_seg_dot<TYPE>(buf1, c_seg, aq_l, ad_l, as_l);
         finish_segment();
-        mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 3 < U);
+        mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 5 < U);
+        advance_load();
+        if (u + 2 >= U) break;
+        mbar_wait(mbar0, P.par & 1u);
+        P.par ^= 1u;
+        acc += mk_stage_dot<TYPE>(stage0, P.sc0, c_seg, GR, g.last_half_off, lane, aq_l, ad_l, as_l);
+        finish_segment();
+        mk_stage_issue<TYPE>(stage0_smem, mbar0, P.sc0, l_ptr, l_seg, nb, lane, u + 6 < U);
+        advance_load();
+        if (u + 3 >= U) break;
+        mbar_wait(mbar0 + 8, (P.par >> 1) & 1u);
+        P.par ^= 2u;
+        acc += mk_stage_dot<TYPE>(stage0 + MK_STAGE_BYTES / 16, P.sc1, c_seg, GR, g.last_half_off, lane, aq_l, ad_l, as_l);
+        finish_segment();
+        mk_stage_issue<TYPE>(stage0_smem + MK_STAGE_BYTES, mbar0 + 8, P.sc1, l_ptr, l_seg, nb, lane, u + 7 < U);
         advance_load();
     }
 }
@@ -556,11 +664,6 @@ __device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsigned xs
     }
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 
 __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
                                                                          unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags, const CommDev comm) {
@@ -569,8 +672,25 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     __shared__ MkPhase s_phs[2];             // phase descriptors, double-buffered: p+1 is fetched while p runs
     __shared__ StreamArgs s_next;            // arguments of the next MATVEC phase (for the look-ahead prefetch)
     __shared__ int s_next_type;
-    MkSeg buf0, buf1;                        // register-resident weight prefetch, live across phases and barriers
-    int prefetched = -1;                     // phase index whose first two segments sit in buf0 / buf1
+    __shared__ __align__(8) unsigned long long s_mbar[MK_WARPS * MK_STAGES];   // one mbarrier per (warp, TMA stage)
+    MkPipe pipe;                             // weight prefetch (registers + TMA stages), live across phases and barriers
+    pipe.par = 0u;
+#if MK_DEEP
+    const bool deep = (flags & 2) != 0;      // TMA stages enabled (host: shared memory budget allows the 128 KB staging area)
+#else
+    constexpr bool deep = false;             // experimental TMA stages compiled out (profiles/r01e: slower -- spills + 128 KB less L1)
+#endif
+    uint8_t* work = smem + (deep ? MK_STAGING : 0);       // per-phase working area (activation arrays, attention tiles)
+    const int4* stage0 = (const int4*)(smem + (threadIdx.x >> 5) * (MK_STAGES * MK_STAGE_BYTES));
+    const unsigned stage0_smem = (unsigned)__cvta_generic_to_shared(stage0);
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&s_mbar[(threadIdx.x >> 5) * MK_STAGES]);
+    if (deep) {
+        if ((threadIdx.x & 31) == 0) { mbar_init(mbar0, 1u); mbar_init(mbar0 + 8, 1u); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+    int prefetched = -1;                     // phase index whose first segments sit in the pipe
     unsigned gen = 0;                        // barriers completed; starts from the value left by the last launch
     if (threadIdx.x == MK_BAR_THREAD) gen = ld_acquire_u32(&bar[32]);
     unsigned xseq = comm.world > 0 ? *comm.seq : 0u;     // exchanges finished so far on this rank (comm.cu)
@@ -581,55 +701,65 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     };
     fetch_desc(0);
     for (int p = 0; p < n_phases; p++) {
-        if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[p] = globaltimer_ns();     // phase start (developer profiling)
+        // developer profiling, 4 stamps per phase from CTA 0 / thread 0: start, activation ready (MATVEC), rows done, arrived + prefetch issued
+        const bool stamp = prof && blockIdx.x == 0 && threadIdx.x == 0;
+        if (stamp) { prof[p * 4] = globaltimer_ns(); prof[p * 4 + 1] = 0; }
         __syncthreads();                     // descriptor p is in shared memory (fetched one phase ago)
         if (p + 1 < n_phases) fetch_desc(p + 1);
         const MkPhase& s_ph = s_phs[p & 1];
+        // arguments of the next MATVEC phase for the look-ahead prefetch: fetched now, consumed after this phase's arrive
+        const int nx = s_ph.next_matvec;
+        const bool look = (flags & 1) && nx > p && nx < n_phases && prefetched != nx && p + 1 < n_phases;
+        if (look) {
+            const int* src = (const int*)&phases[nx].mv;
+            int* dst = (int*)&s_next;
+            for (int i = threadIdx.x; i < (int)(sizeof(StreamArgs) / 4); i += MK_THREADS) dst[i] = src[i];
+            if (threadIdx.x == 0) s_next_type = phases[nx].wtype;
+        }
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
             if (s_ph.wtype == CC_Q8_0) {
-                if (prefetched != p) matvec_prefetch<CC_Q8_0>(s_ph.mv, buf0, buf1);
-                phase_matvec<CC_Q8_0>(s_ph, smem, exp_lut, buf0, buf1, comm, xseq);
+                if (prefetched != p) matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe, deep, stage0_smem, mbar0);
+                phase_matvec<CC_Q8_0>(s_ph, work, exp_lut, pipe, deep, stage0, stage0_smem, mbar0, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr);
             } else {
-                if (prefetched != p) matvec_prefetch<CC_Q4_0>(s_ph.mv, buf0, buf1);
-                phase_matvec<CC_Q4_0>(s_ph, smem, exp_lut, buf0, buf1, comm, xseq);
+                if (prefetched != p) matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe, deep, stage0_smem, mbar0);
+                phase_matvec<CC_Q4_0>(s_ph, work, exp_lut, pipe, deep, stage0, stage0_smem, mbar0, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr);
             }
             break;
         case MK_ATTN:
-            if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)smem, s_red, dyn, exp_lut); else phase_attn<false>(s_ph, (float*)smem, s_red, dyn, exp_lut);
+            if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)work, s_red, dyn, exp_lut); else phase_attn<false>(s_ph, (float*)work, s_red, dyn, exp_lut);
             break;
         case MK_ROWS: phase_rows(s_ph, dyn); break;
         case MK_REDUCE: phase_reduce(s_ph, comm, xseq, false); break;
         case MK_GATHER: phase_reduce(s_ph, comm, xseq, true); break;
         }
+        if (stamp) prof[p * 4 + 2] = globaltimer_ns();
         // look-ahead: request the first two weight segments of the next MATVEC phase before waiting at the barrier, so HBM
         // keeps streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
-        const int nx = s_ph.next_matvec;
         const bool more = p + 1 < n_phases;
         const bool xg = s_ph.xgpu != 0;
-        if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);
-        if ((flags & 1) && nx > p && nx < n_phases && prefetched != nx) {
-            if (!more) __syncthreads();
-            {
-                const int* src = (const int*)&phases[nx].mv;
-                int* dst = (int*)&s_next;
-                for (int i = threadIdx.x; i < (int)(sizeof(StreamArgs) / 4); i += MK_THREADS) dst[i] = src[i];
-                if (threadIdx.x == 0) s_next_type = phases[nx].wtype;
-            }
-            __syncthreads();
-            if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, buf0, buf1); else matvec_prefetch<CC_Q4_0>(s_next, buf0, buf1);
+        if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);       // its bar.sync also publishes s_next (written at phase start)
+        if (look) {
+            if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, pipe, deep, stage0_smem, mbar0); else matvec_prefetch<CC_Q4_0>(s_next, pipe, deep, stage0_smem, mbar0);
             prefetched = nx;
         }
+        if (stamp) prof[p * 4 + 3] = globaltimer_ns();
         if (more) { grid_barrier_wait(bar, gridDim.x, gen, comm, xg ? xseq + 1u : 0u); gen++; if (xg) xseq++; }
     }
     if (comm.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) *comm.seq = xseq;
-    if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases] = globaltimer_ns();
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases * 4] = globaltimer_ns();
 }
 
-size_t cc_mega_smem_for_matvec(int type, int k) {
-    size_t nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
-    return nbp * 40 + 256 + (size_t)k * 8;  // quants | scales | block sums | prologue: reduction scratch, f32 x, f32 norm weights
+// working shared memory of one phase (the TMA staging area of deep mode comes on top, see cc_launch_mega)
+size_t cc_mega_smem_for_phase(const MkPhase& ph) {
+    if (ph.type == MK_MATVEC) {
+        const size_t k = (size_t)ph.mv.k, nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
+        // quants | scales | block sums | prologue: reduction scratch, f32 x, f32 norm weights
+        return nbp * 40 + 256 + (ph.x ? k * 4 : 0) + (ph.x && ph.norm_w ? k * 4 : 0);
+    }
+    if (ph.type == MK_ATTN) return (size_t)(3 * ph.at.hd + ((ph.at.max_len + 8 + 3) & ~3) + 2 * AT_CH * ph.at.hd) * 4 + 64;
+    return 1024;
 }
 
 // developer hook: a table of `n` empty phases -> the pure per-phase floor (descriptor fetch + grid barrier)
@@ -660,8 +790,16 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
 }
 
 int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof, const CommDev* comm) {
-    static const int flags = (getenv("CRABML_MEGA_NOPREFETCH") ? 0 : 1) | (getenv("CRABML_MEGA_FLAGS") ? atoi(getenv("CRABML_MEGA_FLAGS")) : 0);     // developer A/B switches
+    static const int base_flags = (getenv("CRABML_MEGA_NOPREFETCH") ? 0 : 1) | (getenv("CRABML_MEGA_FLAGS") ? atoi(getenv("CRABML_MEGA_FLAGS")) : 0);     // developer A/B switches
     int max_ctas_per_sm = 0;
+    int flags = base_flags;
+    {   // deep prefetch needs the 128 KB TMA staging area in front of the phases' working area
+        cudaFuncAttributes fa;
+        CC_CUDA(dev, cudaFuncGetAttributes(&fa, mega_kernel));
+        const size_t limit = 232448 - fa.sharedSizeBytes;          // 227 KB opt-in maximum per CTA on sm_100
+        if (MK_DEEP && getenv("CRABML_MEGA_DEEP") && (flags & 1) && smem + MK_STAGING <= limit) { flags |= 2; smem += MK_STAGING; }   // experimental, off: profiles/r01e
+        else if (getenv("CRABML_MEGA_PAD") && smem + MK_STAGING <= limit) smem += MK_STAGING;      // developer A/B: shared memory size alone
+    }
     if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, mega_kernel, MK_THREADS, smem));
     CC_REQUIRE(dev, max_ctas_per_sm >= 1, "megakernel does not fit on an SM");

@@ -20,18 +20,27 @@ pos = 0
 for i in range(40):
     r.forward([1 + i], pos, export=False); pos += 1
 dev.synchronize()
-ts = (C.c_uint64 * 4096)(); ty = (C.c_int32 * 4096)(); n = C.c_int32(0)
-dev.check(dev.lib.cc_lazy_mega_profile(dev.handle, ts, ty, 4096, C.byref(n)))
+CAP = 4 * 4096
+ts = (C.c_uint64 * CAP)(); ty = (C.c_int32 * CAP)(); n = C.c_int32(0)
+dev.check(dev.lib.cc_lazy_mega_profile(dev.handle, ts, ty, CAP, C.byref(n)))
 n = n.value
-t = np.array(ts[:n + 1], dtype=np.float64)
+raw = np.array(ts[:(n + 1) * 4], dtype=np.float64).reshape(n + 1, 4)
+t = raw[:, 0]
 d = np.diff(t) / 1e3
-names = {0: "normq", 16 + 3: "qkv matvec(3)", 16 + 1 + 4: "matvec+residual", 16 + 2 + 8: "gate/up silu*mul", 16 + 1: "matvec(1)", 32: "attn", 48: "rows"}
+names = {0: "normq", 16 + 3: "qkv matvec(3)", 16 + 1 + 4: "matvec+residual", 16 + 2 + 8: "gate/up silu*mul", 16 + 1: "matvec(1)", 32: "attn", 48: "rows",
+         16 + 1 + 12: "matvec->exchange", 64: "reduce", 80: "gather"}
 agg = collections.defaultdict(list)
+sub = collections.defaultdict(list)
 for i in range(n):
-    agg[names.get(ty[i], str(ty[i]))].append(d[i])
+    k = names.get(ty[i], str(ty[i]))
+    agg[k].append(d[i])
+    s0, s1, s2, s3 = raw[i]
+    act = (s1 - s0) / 1e3 if s1 > 0 else 0.0            # activation staging / fused prologue (MATVEC only)
+    sub[k].append((act, (s2 - max(s0, s1)) / 1e3, (s3 - s2) / 1e3, (raw[i + 1, 0] - s3) / 1e3))
 print(f"phases {n}, token total {(t[-1] - t[0]) / 1e3:.1f} us (phase time includes the barrier that ends it)")
+print("  CTA 0 breakdown per phase: activation ready | rows of warp 0 done | arrive + look-ahead issue | barrier wait")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-    print(f"  {k:20s} n={len(v):3d}  sum {sum(v):8.1f} us  avg {np.mean(v):6.2f}  min {min(v):6.2f}  max {max(v):6.2f}")
-# the first layers in order
+    m = np.mean(np.array(sub[k]), axis=0)
+    print(f"  {k:20s} n={len(v):3d}  sum {sum(v):8.1f} us  avg {np.mean(v):6.2f}  min {min(v):6.2f}  max {max(v):6.2f}   | {m[0]:5.2f} | {m[1]:5.2f} | {m[2]:5.2f} | {m[3]:5.2f}")
 print("first 10 phases:", [(names.get(ty[i], ty[i]), round(d[i], 2)) for i in range(min(10, n))])
 dev.close()
