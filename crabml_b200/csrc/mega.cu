@@ -483,8 +483,9 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
 // staged in shared memory in chunks of AT_CH positions with ALL loads of a chunk in flight at once: at decode the cost of
 // this phase is HBM/L2 latency, not bandwidth, so round trips are what matters.
 #define AT_CH 64
+#define AT_NBUF 3
 template <bool KV_F16>
-__device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uint8_t* dyn, const uint16_t* exp_lut) {
+__device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uint8_t* dyn, const uint16_t* exp_lut, unsigned abar0, unsigned& apar) {
     const AttnArgs& a = ph.at;
     const int n_heads = a.n_heads, n_kv = a.n_kv, hd = a.hd, rope_dim = a.rope_dim;
     const int64_t seq_stride = a.seq_stride;
@@ -493,27 +494,33 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
     const int kv_len = (int)dynv[1], L = kv_len + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* s_q = sm; float* s_k = sm + hd; float* s_v = sm + 2 * hd; float* s_p = sm + 3 * hd;
-    float* s_kc = sm + 3 * hd + ((a.max_len + 8 + 3) & ~3);      // [AT_CH][hd] K chunk (as f32)
-    float* s_vc = s_kc + AT_CH * hd;                              // [AT_CH][hd] V chunk
+    // AT_NBUF chunk buffers of AT_CH cache rows each (raw bytes: f32 or f16), filled by TMA bulk copies -- the rows of one kv head
+    // are contiguous -- in a K-chunks-then-V-chunks job sequence with AT_NBUF jobs in flight; one mbarrier per buffer.
+    uint8_t* s_buf = (uint8_t*)(sm + 3 * hd + ((a.max_len + 8 + 3) & ~3));
+    const unsigned s_buf_smem = (unsigned)__cvta_generic_to_shared(s_buf);
+    constexpr int ELT = KV_F16 ? 2 : 4;
+    const unsigned buf_bytes = (unsigned)(AT_CH * hd * ELT);
     const int pairs = rope_dim >> 1;
     const int hd4 = hd >> 2;
-    // stage `cnt` cache rows starting at position p0 of kv head g into dst (converted to f32); rows are contiguous
-    auto stage_rows = [&](const void* cache, int g, int p0, int cnt, float* dst) {
-        if (KV_F16) {
-            const __half2* src = (const __half2*)((const __half*)cache + (int64_t)g * seq_stride + (int64_t)p0 * hd);
-            for (int i = threadIdx.x; i < cnt * (hd >> 1); i += MK_THREADS) { float2 f = __half22float2(src[i]); dst[2 * i] = f.x; dst[2 * i + 1] = f.y; }
-        } else {
-            const float4* src = (const float4*)((const float*)cache + (int64_t)g * seq_stride + (int64_t)p0 * hd);
-            float4* d4 = (float4*)dst;
-            for (int i = threadIdx.x; i < cnt * hd4; i += MK_THREADS) d4[i] = src[i];
-        }
+    const int NC = (kv_len + AT_CH - 1) / AT_CH;                  // chunks per pass; jobs 0..NC-1 = K chunks, NC..2NC-1 = V chunks
+    auto issue_job = [&](int g, int j) {                            // one elected thread
+        const int c = j < NC ? j : j - NC;
+        const int p0 = c * AT_CH, cnt = min(AT_CH, kv_len - p0);
+        const uint8_t* src = (const uint8_t*)(j < NC ? a.kcache : a.vcache) + ((int64_t)g * seq_stride + (int64_t)p0 * hd) * ELT;
+        const unsigned bytes = (unsigned)(cnt * hd * ELT), bar = abar0 + 8u * (unsigned)(j % AT_NBUF), dst = s_buf_smem + (unsigned)(j % AT_NBUF) * buf_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
     };
+    auto wait_job = [&](int j) {                                    // all threads, in job order
+        const int bsel = j % AT_NBUF;
+        mbar_wait(abar0 + 8u * (unsigned)bsel, (apar >> bsel) & 1u);
+        apar ^= 1u << bsel;
+    };
+    auto ld_kv = [&](const uint8_t* buf, int idx) -> float { return KV_F16 ? __half2float(((const __half*)buf)[idx]) : ((const float*)buf)[idx]; };
     for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
         const int g = KV_F16 ? h / (n_heads / n_kv) : h % n_kv;
-        // first K chunk (and, when the whole context fits one chunk, the V chunk too) are requested up front
-        const int c0 = min(kv_len, AT_CH);
-        stage_rows(a.kcache, g, 0, c0, s_kc);
-        if (kv_len <= AT_CH) stage_rows(a.vcache, g, 0, c0, s_vc);
+        // the first AT_NBUF jobs are requested up front; every later job is issued as soon as its buffer has been consumed
+        if (threadIdx.x == 0) for (int j = 0; j < min(AT_NBUF, 2 * NC); j++) issue_job(g, j);
         for (int i = threadIdx.x; i < hd; i += MK_THREADS) {
             float qv, kvv;
             if (i < rope_dim) {
@@ -541,16 +548,18 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
             }
         }
         // scores, chunk by chunk; per-lane summation order i = lane, lane+32, ... as in fused.cu
-        for (int p0 = 0; p0 < kv_len; p0 += AT_CH) {
-            const int cnt = min(AT_CH, kv_len - p0);
-            if (p0 > 0) { __syncthreads(); stage_rows(a.kcache, g, p0, cnt, s_kc); __syncthreads(); }
+        for (int j = 0; j < NC; j++) {
+            const int p0 = j * AT_CH, cnt = min(AT_CH, kv_len - p0);
+            const uint8_t* kb = s_buf + (size_t)(j % AT_NBUF) * buf_bytes;
+            wait_job(j);
             for (int s = warp; s < cnt; s += MK_WARPS) {
-                const float* kr = s_kc + s * hd;
                 float acc = 0.0f;
-                for (int i = lane; i < hd; i += 32) acc += (KV_F16 ? __half2float(__float2half_rn(s_q[i])) : s_q[i]) * kr[i];
+                for (int i = lane; i < hd; i += 32) acc += (KV_F16 ? __half2float(__float2half_rn(s_q[i])) : s_q[i]) * ld_kv(kb, s * hd + i);
                 acc = warp_sum(acc);
                 if (lane == 0) s_p[p0 + s] = acc;
             }
+            __syncthreads();                                       // buffer consumed by every warp -> refill it
+            if (threadIdx.x == 0 && j + AT_NBUF < 2 * NC) issue_job(g, j + AT_NBUF);
         }
         if (warp == 0) {                                           // this token's own position
             float acc = 0.0f;
@@ -589,15 +598,18 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
         float accf = 0.0f;
         __half acch = __float2half_rn(0.0f);
         const int d = threadIdx.x;
-        for (int p0 = 0; p0 < kv_len; p0 += AT_CH) {
-            const int cnt = min(AT_CH, kv_len - p0);
-            if (kv_len > AT_CH) { __syncthreads(); stage_rows(a.vcache, g, p0, cnt, s_vc); __syncthreads(); }
+        for (int j = NC; j < 2 * NC; j++) {
+            const int p0 = (j - NC) * AT_CH, cnt = min(AT_CH, kv_len - p0);
+            const uint8_t* vb = s_buf + (size_t)(j % AT_NBUF) * buf_bytes;
+            wait_job(j);
             if (d < hd) {
                 for (int s = 0; s < cnt; s++) {
-                    if (KV_F16) acch = __hadd(acch, __hmul(__float2half_rn(s_vc[s * hd + d]), __float2half_rn(s_p[p0 + s])));
-                    else accf += s_p[p0 + s] * s_vc[s * hd + d];
+                    if (KV_F16) acch = __hadd(acch, __hmul(((const __half*)vb)[s * hd + d], __float2half_rn(s_p[p0 + s])));
+                    else accf += s_p[p0 + s] * ((const float*)vb)[s * hd + d];
                 }
             }
+            __syncthreads();
+            if (threadIdx.x == 0 && j + AT_NBUF < 2 * NC) issue_job(g, j + AT_NBUF);
         }
         float* s_o = s_k;
         __syncthreads();
@@ -673,6 +685,13 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     __shared__ StreamArgs s_next;            // arguments of the next MATVEC phase (for the look-ahead prefetch)
     __shared__ int s_next_type;
     __shared__ __align__(8) unsigned long long s_mbar[MK_WARPS * MK_STAGES];   // one mbarrier per (warp, TMA stage)
+    __shared__ __align__(8) unsigned long long s_abar[AT_NBUF];                // attention chunk buffers (TMA completion)
+    unsigned apar = 0u;                      // per-buffer wait parity of the attention chunk pipeline
+    const unsigned abar0 = (unsigned)__cvta_generic_to_shared(&s_abar[0]);
+    if (threadIdx.x == 0) { for (int i = 0; i < AT_NBUF; i++) mbar_init(abar0 + 8u * i, 1u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
     MkPipe pipe;                             // weight prefetch (registers + TMA stages), live across phases and barriers
     pipe.par = 0u;
 #if MK_DEEP
@@ -728,7 +747,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             }
             break;
         case MK_ATTN:
-            if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)work, s_red, dyn, exp_lut); else phase_attn<false>(s_ph, (float*)work, s_red, dyn, exp_lut);
+            if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar); else phase_attn<false>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar);
             break;
         case MK_ROWS: phase_rows(s_ph, dyn); break;
         case MK_REDUCE: phase_reduce(s_ph, comm, xseq, false); break;
@@ -758,7 +777,7 @@ size_t cc_mega_smem_for_phase(const MkPhase& ph) {
         // quants | scales | block sums | prologue: reduction scratch, f32 x, f32 norm weights
         return nbp * 40 + 256 + (ph.x ? k * 4 : 0) + (ph.x && ph.norm_w ? k * 4 : 0);
     }
-    if (ph.type == MK_ATTN) return (size_t)(3 * ph.at.hd + ((ph.at.max_len + 8 + 3) & ~3) + 2 * AT_CH * ph.at.hd) * 4 + 64;
+    if (ph.type == MK_ATTN) return (size_t)(3 * ph.at.hd + ((ph.at.max_len + 8 + 3) & ~3) + AT_NBUF * AT_CH * ph.at.hd) * 4 + 64;
     return 1024;
 }
 
