@@ -394,12 +394,24 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         const uint8_t* act = (const uint8_t*)A.act;
         const int4* gq = (const int4*)act;
         int4* sq4 = (int4*)s_q;
-        for (int i = threadIdx.x; i < nbp * 2; i += MK_THREADS) sq4[i] = i < nb * 2 ? __ldcg(gq + i) : make_int4(0, 0, 0, 0);
         const float* gd = (const float*)(act + ((k + 15) & ~15));
         const int* gs = (const int*)(act + ((k + 15) & ~15) + ((nb * 4 + 15) & ~15));
-        for (int i = threadIdx.x; i < nbp; i += MK_THREADS) {
-            s_d[i] = i < nb ? __ldcg(gd + i) : 0.0f;
-            if constexpr (TYPE == CC_Q4_0) s_s[i] = i < nb ? __ldcg(gs + i) : 0;
+        if (nbp <= MK_THREADS) {           // every load of the thread is issued before its first store (one L2 round trip, not three)
+            const int i0 = threadIdx.x, i1 = threadIdx.x + MK_THREADS;
+            const int4 z4 = make_int4(0, 0, 0, 0);
+            const int4 qa = i0 < nb * 2 ? __ldcg(gq + i0) : z4, qb = i1 < nb * 2 ? __ldcg(gq + i1) : z4;
+            const float dv = i0 < nb ? __ldcg(gd + i0) : 0.0f;
+            int sv = 0;
+            if constexpr (TYPE == CC_Q4_0) sv = i0 < nb ? __ldcg(gs + i0) : 0;
+            if (i0 < nbp * 2) sq4[i0] = qa;
+            if (i1 < nbp * 2) sq4[i1] = qb;
+            if (i0 < nbp) { s_d[i0] = dv; if constexpr (TYPE == CC_Q4_0) s_s[i0] = sv; }
+        } else {
+            for (int i = threadIdx.x; i < nbp * 2; i += MK_THREADS) sq4[i] = i < nb * 2 ? __ldcg(gq + i) : make_int4(0, 0, 0, 0);
+            for (int i = threadIdx.x; i < nbp; i += MK_THREADS) {
+                s_d[i] = i < nb ? __ldcg(gd + i) : 0.0f;
+                if constexpr (TYPE == CC_Q4_0) s_s[i] = i < nb ? __ldcg(gs + i) : 0;
+            }
         }
     }
     __syncthreads();
@@ -409,6 +421,19 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
     const int* as_l = s_s + lane;
     float acc = 0.0f, first = 0.0f;
     int c_i = 0, c_seg = 0;
+    // Epilogues that need a value from memory (the residual, or the exp LUT entry of silu) are finished ONE ROW LATER: the load
+    // is issued when the row's dot is known and consumed after the next row, so the warp never stalls an L2 round trip with its
+    // weight stream idle (in-order issue).  lane 0 only.
+    float pend_a = 0.0f, pend_b = 0.0f, pend_res = 0.0f;
+    unsigned short pend_lut = 0;
+    int pend_row = -1;
+    auto flush_pending = [&]() {
+        if (lane == 0 && pend_row >= 0) {
+            if (pair) M.out[0][pend_row] = (pend_a / (1.0f + h2f_bits(pend_lut))) * pend_b;
+            else M.out[0][pend_row] = pend_a + pend_res;
+        }
+        pend_row = -1;
+    };
     auto finish_segment = [&]() {
         if (++c_seg < NSEG) return;
         c_seg = 0;
@@ -417,17 +442,21 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         const int i = c_i++;
         if (pair) {
             if ((i & 1) == 0) { first = r; return; }
+            flush_pending();
             if (lane == 0) {
-                float gt = first;
-                float nexp = h2f_bits(exp_lut[f2h_bits(-gt)]);
-                M.out[0][gw + (i >> 1) * TW] = (gt / (1.0f + nexp)) * r;
+                pend_a = first; pend_b = r; pend_row = gw + (i >> 1) * TW;
+                pend_lut = exp_lut[f2h_bits(-first)];
             }
+            return;
+        }
+        if (A.epilogue == 1) {                 // single matrix: out = dot + residual (llama2.rs:266,636)
+            flush_pending();
+            if (lane == 0) { pend_a = r; pend_row = gw + i * TW; pend_res = ldcg_f(A.residual + pend_row); }
             return;
         }
         if (lane == 0) {
             int mat = 0, rr = gw + i * TW;
             if (M.n > 1 && rr >= M.m[0]) { rr -= M.m[0]; mat = 1; if (M.n > 2 && rr >= M.m[1]) { rr -= M.m[1]; mat = 2; } }
-            if (A.epilogue == 1) r = r + ldcg_f(A.residual + rr);
             if (A.epilogue == 3) {         // partial row -> slot[rank] of every GPU's exchange window (NVLink peer stores)
                 const size_t off = ((size_t)((xseq + 1u) & 1u) * CC_COMM_MAX_RANKS + comm.rank) * CC_COMM_MAX_ELEMS + rr;
                 for (int pr = 0; pr < comm.world; pr++) comm.data[pr][off] = r;
@@ -449,6 +478,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
             mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 3 < U);
             advance_load();
         }
+        flush_pending();
         return;
     }
     // deep: four segments in flight per warp, slots rotate register 0, register 1, TMA stage 0, TMA stage 1
@@ -477,6 +507,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         mk_stage_issue<TYPE>(stage0_smem + MK_STAGE_BYTES, mbar0 + 8, P.sc1, l_ptr, l_seg, nb, lane, u + 7 < U);
         advance_load();
     }
+    flush_pending();
 }
 
 // ---- ATTN phase: arithmetic of fused.cu attn_decode_kernel, heads dealt to CTAs.  The K (then V) rows of the head are
@@ -723,17 +754,19 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         // developer profiling, 4 stamps per phase from CTA 0 / thread 0: start, activation ready (MATVEC), rows done, arrived + prefetch issued
         const bool stamp = prof && blockIdx.x == 0 && threadIdx.x == 0;
         if (stamp) { prof[p * 4] = globaltimer_ns(); prof[p * 4 + 1] = 0; }
-        __syncthreads();                     // descriptor p is in shared memory (fetched one phase ago)
-        if (p + 1 < n_phases) fetch_desc(p + 1);
+        __syncthreads();                     // descriptor p is in shared memory (stored one phase ago)
         const MkPhase& s_ph = s_phs[p & 1];
-        // arguments of the next MATVEC phase for the look-ahead prefetch: fetched now, consumed after this phase's arrive
+        // Descriptor p+1 and the arguments of the next MATVEC phase (look-ahead prefetch) are LOADED now, into one register each,
+        // and STORED to shared memory after the phase body: a load followed directly by its st.shared would block the thread for
+        // an L2 round trip (in-order issue) before it could issue the phase's own loads.
+        static_assert(sizeof(MkPhase) / 4 <= MK_THREADS && sizeof(StreamArgs) / 4 + 1 <= MK_THREADS, "descriptor does not fit one word per thread");
         const int nx = s_ph.next_matvec;
         const bool look = (flags & 1) && nx > p && nx < n_phases && prefetched != nx && p + 1 < n_phases;
+        int desc_w = 0, next_w = 0;
+        if (p + 1 < n_phases && threadIdx.x < sizeof(MkPhase) / 4) desc_w = ((const int*)(phases + p + 1))[threadIdx.x];
         if (look) {
-            const int* src = (const int*)&phases[nx].mv;
-            int* dst = (int*)&s_next;
-            for (int i = threadIdx.x; i < (int)(sizeof(StreamArgs) / 4); i += MK_THREADS) dst[i] = src[i];
-            if (threadIdx.x == 0) s_next_type = phases[nx].wtype;
+            if (threadIdx.x < sizeof(StreamArgs) / 4) next_w = ((const int*)&phases[nx].mv)[threadIdx.x];
+            else if (threadIdx.x == sizeof(StreamArgs) / 4) next_w = phases[nx].wtype;
         }
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
@@ -754,6 +787,11 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         case MK_GATHER: phase_reduce(s_ph, comm, xseq, true); break;
         }
         if (stamp) prof[p * 4 + 2] = globaltimer_ns();
+        if (p + 1 < n_phases && threadIdx.x < sizeof(MkPhase) / 4) ((int*)&s_phs[(p + 1) & 1])[threadIdx.x] = desc_w;
+        if (look) {
+            if (threadIdx.x < sizeof(StreamArgs) / 4) ((int*)&s_next)[threadIdx.x] = next_w;
+            else if (threadIdx.x == sizeof(StreamArgs) / 4) s_next_type = next_w;
+        }
         // look-ahead: request the first two weight segments of the next MATVEC phase before waiting at the barrier, so HBM
         // keeps streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
         const bool more = p + 1 < n_phases;
