@@ -248,7 +248,9 @@ __device__ __forceinline__ MkGeo mk_geo(const StreamArgs& A) {
     MkGeo g;
     const int warp = threadIdx.x >> 5;
     g.nb = A.k >> 5; g.GR = (g.nb + 31) >> 5; g.NSEG = (g.GR + MK_SEG - 1) / MK_SEG;
-    g.gw = blockIdx.x * MK_WARPS + warp; g.TW = gridDim.x * MK_WARPS;
+    // warp-major numbering: when rows do not divide by the warp count, every SM gets the same mix of k- and (k+1)-row warps
+    // (CTA-major numbering left the last SMs with half the work of the first ones)
+    g.gw = warp * gridDim.x + blockIdx.x; g.TW = gridDim.x * MK_WARPS;
     g.pair = A.epilogue == 2;
     const StreamMats& M = A.mats;
     const int m_cat = g.pair ? M.m[0] : M.m[0] + (M.n > 1 ? M.m[1] : 0) + (M.n > 2 ? M.m[2] : 0);
