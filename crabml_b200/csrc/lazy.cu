@@ -143,10 +143,19 @@ struct Fuser {
     size_t rope_off = (size_t)-1; int64_t rope_pos = -1; int rope_hd = 0, rope_dim = 0;
 
     bool is(size_t i, int kind) const { return i < q.size() && !q[i].done && q[i].kind == kind; }
-    // no op after `from` touches buf, and nobody outside the queue holds it
+    std::unordered_map<cc_buf*, size_t> last_use;      // buffer -> index of the last queued op that touches it (built once per flush)
+    void index_uses() {
+        last_use.reserve(q.size() * 2);
+        for (size_t j = 0; j < q.size(); j++) {
+            if (q[j].a.buf) last_use[q[j].a.buf] = j;
+            if (q[j].b.buf) last_use[q[j].b.buf] = j;
+            if (q[j].out) last_use[q[j].out] = j;
+        }
+    }
+    // no op at or after `from` touches buf, and nobody outside the queue holds it
     bool dead_after(cc_buf* b, size_t from) const {
-        for (size_t j = from; j < q.size(); j++)
-            if (q[j].a.buf == b || q[j].b.buf == b || q[j].out == b) return false;
+        auto lu = last_use.find(b);
+        if (lu != last_use.end() && lu->second >= from) return false;
         auto it = lz->qrefs.find(b);
         int held = it == lz->qrefs.end() ? 0 : it->second;
         return b->refs.load() == held;
@@ -425,6 +434,7 @@ struct Fuser {
     }
 
     void run() {
+        index_uses();
         size_t i = 0;
         while (i < q.size()) {
             if (q[i].done) { i++; continue; }
@@ -527,7 +537,6 @@ int cc_lazy_flush(cc_device* dev) {
             if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
             if (!rc) {
                 if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue : 0)); }
-                if (use_mega) cudaMemsetAsync(lz->bar_dev, 0, 4096, dev->stream);      // (captured) barrier counters restart from 0 in every replay
                 rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem,
                                                P.phases.size() < 4000 ? lz->prof_dev : nullptr, cc_comm_dev(dev)) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);

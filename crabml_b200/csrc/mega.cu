@@ -36,8 +36,9 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm vo
 //   ...      the other warps may already issue the next phase's weight prefetch;
 //   wait   : CTA 0 watches the counter reach (gen+1) * nblocks and publishes the generation word; everyone else spins on
 //            the generation with ld.acquire; then bar.sync.
-// Layout (u32 words on separate 128-byte lines): [0] arrival counter, [32] generation.  Counters are zeroed by a memset node
-// at the head of every graph replay, so `gen` starts at 0.
+// Layout (u32 words on separate 128-byte lines): [0] arrival counter, [32] generation.  Both are monotonic ACROSS launches (u32
+// wrap-around included: only equality is tested): a launch starts from the generation the previous one left, so a graph
+// replay needs no reset node in front of the kernel.
 __device__ __forceinline__ void red_add_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 #define MK_BAR_THREAD (MK_THREADS - 1)
 __device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen, bool xgpu = false) {

@@ -20,6 +20,11 @@ pos = 0
 for i in range(40):
     r.forward([1 + i], pos, export=False); pos += 1
 dev.synchronize()
+dev.timer_begin()
+for i in range(40):
+    r.forward([100 + i], pos, export=False); pos += 1
+ms = dev.timer_end()
+print(f"40 tokens back to back: {ms / 40 * 1e3:.1f} us per token by CUDA events (kernel time below + inter-launch gap)")
 CAP = 4 * 4096
 ts = (C.c_uint64 * CAP)(); ty = (C.c_int32 * CAP)(); n = C.c_int32(0)
 dev.check(dev.lib.cc_lazy_mega_profile(dev.handle, ts, ty, CAP, C.byref(n)))
