@@ -52,17 +52,22 @@ __device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblo
 // barrier thread, once every local CTA has arrived (all partial rows are stored in the peers' slots), publishes xseq in each
 // peer's flag word, waits for every peer's xseq in its own flag words, and only then opens the local barrier.
 __device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblocks, unsigned gen, const CommDev& comm, unsigned xseq = 0) {
-    if (threadIdx.x == MK_BAR_THREAD) {
+    const int lane = threadIdx.x & 31;
+    if ((threadIdx.x >> 5) == MK_WARPS - 1) {              // the warp of MK_BAR_THREAD (its lane 31)
         if (blockIdx.x == 0) {
-            const unsigned target = (gen + 1u) * nblocks;
-            while (ld_acquire_u32(&bar[0]) != target) { }
-            if (xseq) {
-                __threadfence_system();
-                for (int p = 0; p < comm.world; p++) cc_st_release_sys(comm.flag[p] + comm.rank * 32, xseq);
-                for (int p = 0; p < comm.world; p++) { const unsigned* f = comm.flag[comm.rank] + p * 32; while ((int)(cc_ld_acquire_sys(f) - xseq) < 0) { } }
+            if (lane == 31) { const unsigned target = (gen + 1u) * nblocks; while (ld_acquire_u32(&bar[0]) != target) { } }
+            if (xseq) {                                     // kernel-uniform: the whole warp takes this branch together
+                __syncwarp();                               // every local CTA has arrived: all partial rows are in the peers' slots
+                if (lane < comm.world) {                    // one lane per peer: publish and poll in parallel, not rank after rank
+                    __threadfence_system();
+                    cc_st_release_sys(comm.flag[lane] + comm.rank * 32, xseq);
+                    const unsigned* f = comm.flag[comm.rank] + lane * 32;
+                    while ((int)(cc_ld_acquire_sys(f) - xseq) < 0) { }
+                }
+                __syncwarp();
             }
-            st_release_u32(&bar[32], gen + 1u);
-        } else {
+            if (lane == 31) st_release_u32(&bar[32], gen + 1u);
+        } else if (lane == 31) {
             while (ld_acquire_u32(&bar[32]) != gen + 1u) { }
         }
     }
