@@ -39,6 +39,20 @@ TRAFFIC = {("llama2-7b-q8_0", 1): 7059924000 + 11929600}     # profiles/r01f_meg
 TYPE_ID = {"Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q8_0": 8, "Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}
 
 
+def usable_cpus():
+    """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota (spin-waiting workers beyond the
+    quota get throttled by CFS and make the CPU arm erratic)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -107,12 +121,15 @@ def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 3):
     probe_w = synth_weight(wt, 2048, dim, SEED, 99, R.synth_scale(wt, dim))
     probe_x = np.random.default_rng(0).standard_normal(dim).astype(np.float32)
     threads, best = 1, float("inf")
-    for cand in sorted({c for c in (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128, oc.hw_threads()) if c <= oc.hw_threads()}):
+    cpus = min(usable_cpus(), oc.hw_threads())
+    for cand in sorted({c for c in (1, 2, 4, 8, 12, 16, 24, 32, 48, 64, 96, 128, cpus) if c <= cpus}):
         oc.gemv(wt, probe_w, 2048, dim, probe_x, threads=cand, flags=oc.ORDER_AVX2)
-        t0 = time.perf_counter()
-        for _ in range(5):
-            oc.gemv(wt, probe_w, 2048, dim, probe_x, threads=cand, flags=oc.ORDER_AVX2)
-        dt = time.perf_counter() - t0
+        dt = float("inf")
+        for _ in range(3):                       # best of 3 batches of 5
+            t0 = time.perf_counter()
+            for _ in range(5):
+                oc.gemv(wt, probe_w, 2048, dim, probe_x, threads=cand, flags=oc.ORDER_AVX2)
+            dt = min(dt, time.perf_counter() - t0)
         if dt < best * 0.97:
             threads, best = cand, dt
         elif dt > best * 1.3:
@@ -159,7 +176,7 @@ def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 3):
     per_token = per_layer * conf.n_layers + max(rest, 0.0)
     sample = (f"{n_sample_layers} of {conf.n_layers} layers + classifier of {workload} (same synthetic weights, seed {SEED:#x}), "
               f"best of {budget_tokens} tokens after 1 warm-up, per-layer time x {conf.n_layers} + classifier; AVX2-order restatement, "
-              f"{threads} threads (fastest count of an ascending probe on this host, {oc.hw_threads()} hardware threads)")
+              f"{threads} threads (fastest count of an ascending probe; {cpus} usable CPUs = affinity capped by the cgroup quota, {oc.hw_threads()} hardware threads)")
     return 1.0 / per_token, threads, sample, per_token
 
 

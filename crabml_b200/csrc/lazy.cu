@@ -40,8 +40,9 @@ struct GraphEntry { cudaGraphExec_t exec = nullptr; size_t dyn_bytes = 0; uint64
 struct LazyState {
     std::vector<LOp> q;
     std::unordered_map<cc_buf*, int> qrefs;
-    uint8_t* dyn_host[2] = {nullptr, nullptr};     // pinned, alternated so the host can build token t+1 while t runs
-    cudaEvent_t dyn_ev[2] = {nullptr, nullptr};
+#define LZ_DYN_SLOTS 8                               // tokens the host may run ahead of the GPU (absorbs host scheduling hiccups)
+    uint8_t* dyn_host[LZ_DYN_SLOTS] = {nullptr};   // pinned, rotated so the host can build tokens t+1.. while t runs
+    cudaEvent_t dyn_ev[LZ_DYN_SLOTS] = {nullptr};
     int dyn_slot = 0;
     uint8_t* dyn_dev = nullptr;
     size_t dyn_cap = 1 << 16;
@@ -73,7 +74,7 @@ static bool vcontig(const LView& v) {
 
 LazyState* cc_lazy_create(cc_device* dev) {
     LazyState* lz = new LazyState();
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < LZ_DYN_SLOTS; i++)
         if (cudaMallocHost(&lz->dyn_host[i], lz->dyn_cap) != cudaSuccess || cudaEventCreateWithFlags(&lz->dyn_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete lz; return nullptr; }
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
     if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 4 * 4096);
@@ -86,7 +87,7 @@ void cc_lazy_destroy(cc_device* dev) {
     for (auto& op : lz->q) { if (op.a.buf) cc_tensor_release(op.a.buf); if (op.b.buf) cc_tensor_release(op.b.buf); if (op.out) cc_tensor_release(op.out); }
     for (auto& kv : lz->cache) { cudaGraphExecDestroy(kv.second.exec); if (kv.second.phases_dev) cudaFree(kv.second.phases_dev); }
     if (lz->bar_dev) cudaFree(lz->bar_dev);
-    for (int i = 0; i < 2; i++) { if (lz->dyn_host[i]) cudaFreeHost(lz->dyn_host[i]); if (lz->dyn_ev[i]) cudaEventDestroy(lz->dyn_ev[i]); }
+    for (int i = 0; i < LZ_DYN_SLOTS; i++) { if (lz->dyn_host[i]) cudaFreeHost(lz->dyn_host[i]); if (lz->dyn_ev[i]) cudaEventDestroy(lz->dyn_ev[i]); }
     if (lz->dyn_dev) cudaFree(lz->dyn_dev);
     for (int i = 0; i < 2; i++) if (lz->act[i]) cudaFree(lz->act[i]);
     delete lz;
@@ -505,8 +506,8 @@ int cc_lazy_flush(cc_device* dev) {
     if (P.dyn.size() > lz->dyn_cap) rc = cc_fail(dev, CC_ERR_UNSUPPORTED, "lazy: dynamic argument block too large");
     if (!rc && !P.dyn.empty()) {
         const int s = lz->dyn_slot;
-        lz->dyn_slot ^= 1;
-        cudaEventSynchronize(lz->dyn_ev[s]);          // the copy that last read this slot (two flushes ago) is long done
+        lz->dyn_slot = (s + 1) % LZ_DYN_SLOTS;
+        cudaEventSynchronize(lz->dyn_ev[s]);          // the copy that last read this slot (LZ_DYN_SLOTS flushes ago) is long done
         memcpy(lz->dyn_host[s], P.dyn.data(), P.dyn.size());
         if (cudaMemcpyAsync(lz->dyn_dev, lz->dyn_host[s], P.dyn.size(), cudaMemcpyHostToDevice, dev->stream) != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: dyn upload failed");
         cudaEventRecord(lz->dyn_ev[s], dev->stream);
