@@ -250,8 +250,11 @@ struct Fuser {
         void* act = lz->act[act_sel];
         cc_device* d = dev;
         // the normalised f32 row only has to be materialised if something other than the following matvecs reads it
+        // (only matvecs the streaming kernel will take consume the quantised scratch; any other reader -- a K-quant or batched
+        // matvec falling back to its eager kernel -- needs the f32 row)
         size_t end = j + 2;
-        while (is(end, L_MATVEC) && q[end].b.buf == rn.a.buf) end++;
+        while (is(end, L_MATVEC) && q[end].b.buf == rn.a.buf && cc_stream_supported(q[end].a.buf->dtype, q[end].a.shape[1]) &&
+               vlen(q[end].b) == q[end].a.shape[1] && vcontig(q[end].b)) end++;
         const bool write_back = !dead_after(rn.a.buf, end);
         P.S(0x2001); P.SP(x); P.SP(og); P.SP(w); P.SP(act); P.S((uint64_t)n); uint32_t eb; memcpy(&eb, &eps, 4); P.S(eb); P.S(write_back);
         P.steps.push_back([=](uint8_t*) { return cc_launch_normq(d, x, og, w, eps, n, act, write_back); });

@@ -150,14 +150,17 @@ def test_lazy_mode_matches_eager_ops_through_python_mirror(fixture_path):
         dev.close()
 
 
-def test_lazy_7b_shaped_layer(fixture_path=None):
+@pytest.mark.parametrize("wt,ct", [(oc.Q8_0, oc.Q8_0), (oc.Q4_0, oc.Q6_K), (oc.Q4_K, oc.Q6_K)])
+def test_lazy_7b_shaped_layer(wt, ct):
+    """Every execution mode on the same model.  The K-quant rows do not take the streaming kernel: they check that the fuser
+    hands the f32 normalised row (not only the Q8_0 scratch) to matvecs that fall back to their eager kernels."""
     from crabml_b200 import runner as R
     conf = R.LlamaConfig(32, 32, 2, 4096, 11008, 4096, 32000, 1e-5, 128)
     res = {}
     for lazy in (0, 1, 2):
         dev = make_device(lazy=lazy)
         try:
-            w = R.synthetic_weights(dev, conf, oc.Q8_0, oc.Q8_0, seed=7)
+            w = R.synthetic_weights(dev, conf, wt, ct, seed=7)
             r = R.LlamaRunner(dev, conf, w, 16)
             res[lazy] = np.stack([r.forward([t], p).copy() for p, t in enumerate([1, 777, 31999, 5, 6])])
             if lazy:
