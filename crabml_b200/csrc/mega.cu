@@ -873,7 +873,19 @@ int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, cons
     CommDev cd;
     memset(&cd, 0, sizeof(cd));
     if (comm) cd = *comm;
-    mega_kernel<<<grid, MK_THREADS, smem, dev->stream>>>(phases_dev, n_phases, dyn_dev, bar_dev, dev->exp_lut, prof, flags, cd);
+    // The grid barrier needs every CTA resident at once.  On a GPU this process owns, a plain launch of sm_count CTAs (1 per SM)
+    // is co-resident by construction.  With another tenant on the same GPU (a second process, MPS) a partially scheduled grid
+    // would spin forever: CRABML_MEGA_COOP=1 adds the cooperative launch attribute (all-or-nothing placement).  It is opt-in
+    // because a cooperative kernel node costs ~1.3 ms per graph launch on this driver (274 vs 416 tok/s, same call).
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MK_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = dev->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = getenv("CRABML_MEGA_COOP") ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const uint16_t* lut = dev->exp_lut;
+    CC_CUDA(dev, cudaLaunchKernelEx(&cfg, mega_kernel, phases_dev, n_phases, dyn_dev, bar_dev, lut, prof, flags, (const CommDev)cd));
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }
