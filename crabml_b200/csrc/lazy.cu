@@ -10,7 +10,7 @@
 //      (position, KV length, token ids, RoPE table) live in a small device buffer `dyn` that the kernels read;
 //   3. first time a hash is seen the launches are stream-captured into a CUDA graph (programmatic-dependent-launch edges
 //      included); afterwards a token = one 1-2 KB H2D copy of `dyn` + one cudaGraphLaunch.
-// The activation pool hands out the same pointers for the same call sequence (LIFO free lists), which is what makes the
+// The activation pool hands out the same pointers for the same call sequence (lowest free address first), which is what makes the
 // hash stable from token to token.
 #include <math.h>
 #include <stdlib.h>

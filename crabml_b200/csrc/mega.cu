@@ -1,13 +1,16 @@
 // mega.cu -- one persistent kernel per token ("megakernel") for the fused decode path.
 //
-// Why: profiles/r01c/r01d -- on B200 a kernel boundary costs ~4-5 us for a full-GPU streaming kernel (drain, launch
-// latency, ramp-up) and ~2-3 us for a tiny one; a fused Llama-2-7B token still has ~260 of them (~1 ms), as much as the
-// 1.05 ms the weights need at HBM speed.  Here the whole token is ONE launch of 2 CTAs per SM that walks a table of
-// phases (built by lazy.cu from the recorded trait calls) separated by grid-wide barriers (~1 us each):
-//     NORMQ   [dup] + rms_norm * w + Q8_0 quantisation          (slices of blocks per CTA, rms recomputed per CTA)
-//     MATVEC  streaming matvec over 1-3 matrices + epilogue     (same body as matvec_stream.cu)
-//     ATTN    rope + KV append + attention + output quantise    (one CTA per head)
+// Why: profiles/r01c -- on B200 a kernel boundary costs ~4-5 us for a full-GPU streaming kernel (drain, launch latency,
+// ramp-up) and ~2-3 us for a tiny one; a fused Llama-2-7B token still has ~260 of them (~1 ms), as much as the 1.05 ms the
+// weights need at HBM speed.  Here the whole token is ONE launch of one 512-thread CTA per SM that walks a table of
+// phases (built by lazy.cu from the recorded trait calls) separated by grid-wide barriers (2.15 us each, measured):
+//     MATVEC  streaming matvec over 1-3 matrices + epilogue, optionally with a fused prologue ([dup] + rms_norm * w + Q8_0
+//             quantisation of the input row, recomputed by every CTA) and, on the sharded path, the exchange with the other GPUs
+//     NORMQ   the same normalise + quantise as a phase of its own (only when the f32 row must be materialised)
+//     ATTN    rope + KV append + attention + output quantise    (one CTA per head, K/V chunks through a TMA pipeline)
 //     ROWS    copy_rows_from (embedding row dequantisation)
+//     REDUCE / GATHER   second half of an exchange when it cannot fold into the next MATVEC prologue
+// Measurements and the per-phase time breakdown: profiles/r01f_megakernel_ncu.md.
 // Data written by one CTA and read by another in a later phase is always read with ld.global.cg (L2), never through
 // the non-coherent L1.  All CTAs execute the same number of barriers.
 #include <stdlib.h>
