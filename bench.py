@@ -198,10 +198,7 @@ def run_reference(args, rank, world):
 
 # --------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
-    import ctypes as C
-
     from crabml_b200 import CudaTensor, CudaTensorDevice
-    from crabml_b200 import capi
     from crabml_b200 import runner as R
 
     dist = None

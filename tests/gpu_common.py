@@ -1,8 +1,6 @@
 import numpy as np
-import pytest
 
-from oracle import oracle as oc
-from oracle.tensor_ref import OracleDevice, OracleTensor
+from oracle.tensor_ref import OracleTensor
 
 
 def make_device(**kw):

@@ -4,7 +4,6 @@ north_star: logits within 1e-3 relative; golden generations of llama2.rs:673-703
 import numpy as np
 import pytest
 
-from oracle import oracle as oc
 from oracle.llama_replay import GGUFModel, Llama2Runner, LlamaTokenizer, decode_text, load_weights
 from oracle.tensor_ref import OracleDevice, OracleTensor
 from tests.gpu_common import make_device

@@ -3,7 +3,6 @@ import numpy as np
 import pytest
 
 from oracle import oracle as oc
-from oracle.tensor_ref import OracleDevice, OracleTensor
 from tests.blockgen import random_weight
 from tests.gpu_common import make_device
 

@@ -9,7 +9,6 @@ import sys
 import numpy as np
 import pytest
 
-from oracle import oracle as oc
 from tests.gpu_common import make_device
 
 pytestmark = pytest.mark.gpu
