@@ -1,0 +1,193 @@
+"""Host logic of the product's C++ Llama2Runner replay (crabml_b200/csrc/host/llama2_runner.cpp) on CPU: built against a mock
+of the C ABI that only records calls, its op trace must equal, call for call (op, shapes, strides, dtypes, scalars, tap names),
+the trace of the Python replay of the reference's forward() (oracle/llama_replay.py -- the replay that reproduces the
+reference's golden generations in tests/test_oracle_golden_text.py) run on a trace-only tensor class.  Covers the
+single-device order (llama2.rs:184-281, 527-638) and the sharded insertion points (all_reduce after wo / ffn_down,
+all_gather of the logits)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from crabml_b200 import capi, sharding
+from oracle import oracle as oc
+from oracle.llama_replay import Llama2Runner, LlamaConfig as OConf, LlamaWeights
+from oracle.tensor_ref import TensorStrider
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _f(x):
+    return "%.9g" % float(np.float32(x))
+
+
+class TraceDevice:
+    def __init__(self):
+        self.trace = []
+
+
+class TraceTensor:
+    """The Tensor trait with metadata only: every data op appends one line to device.trace (format of tests/host/mock_abi.cpp)."""
+
+    def __init__(self, strider, dtype, device, capacity):
+        self._strider, self._dtype, self.device, self.capacity = strider, dtype, device, capacity
+
+    def V(self):
+        st = self._strider
+        return f"[{','.join(map(str, st.shape))}]/[{','.join(map(str, st.strides))}]:{self._dtype}"
+
+    def log(self, s): self.device.trace.append(s)
+
+    @classmethod
+    def weight(cls, shape, dtype, device):
+        return cls(TensorStrider(shape), dtype, device, int(np.prod(shape)))
+
+    @classmethod
+    def alloc(cls, shape, dtype, device):
+        device.trace.append(f"alloc [{','.join(map(str, shape))}]:{dtype}")
+        return cls(TensorStrider(shape), dtype, device, int(np.prod(shape)))
+
+    def dtype(self): return self._dtype
+    def shape(self): return list(self._strider.shape)
+    def strider(self): return self._strider
+    def _with(self, st): return TraceTensor(st, self._dtype, self.device, self.capacity)
+
+    def resize(self, axis, n):
+        ns = self.shape(); ns[axis] = n
+        assert int(np.prod(ns)) <= self.capacity
+        return self._with(self._strider.resize(ns))
+
+    def with_strider(self, st): return self._with(st.clone())
+    def reshape(self, shape): return self._with(self._strider.reshape(list(shape)))
+    def transpose(self, dims): return self._with(self._strider.transpose(list(dims)))
+    def with_name(self, name): self.log(f"tap {name}"); return self
+
+    def contiguous(self):
+        if self._strider.is_contiguous():
+            return self
+        self.log(f"contiguous {self.V()}")
+        return TraceTensor(TensorStrider(self.shape()), self._dtype, self.device, self._strider.len())
+
+    def concatenate(self, rhs, axis):
+        self.log(f"concatenate dst={self.V()} src={rhs.V()} axis={axis}")
+        ns = self.shape(); ns[axis] += rhs.shape()[axis]
+        self._strider = self._strider.resize(ns)
+
+    def copy_rows_from(self, src, rows): self.log(f"copy_rows_from dst={self.V()} src={src.V()} rows=[{','.join(map(str, rows))}]")
+    def export(self): self.log(f"export {self.V()} n={self._strider.len()}"); return np.zeros(self._strider.len(), np.float32)
+    def dup(self): self.log(f"dup {self.V()}"); return TraceTensor(TensorStrider(self.shape()), oc.F32, self.device, self._strider.len())
+    def rope_inplace(self, mode, pos, dims): self.log(f"rope {self.V()} mode={mode} pos={pos} dims={dims}"); return self
+    def rms_norm_inplace(self, eps): self.log(f"rms_norm {self.V()} eps={_f(eps)}"); return self
+    def softmax_inplace(self, axis): self.log(f"softmax {self.V()} axis={axis}"); return self
+    def silu_inplace(self): self.log(f"silu {self.V()}"); return self
+    def mul_inplace(self, r): self.log(f"mul {self.V()} rhs={r.V()}"); return self
+    def add_inplace(self, r): self.log(f"add {self.V()} rhs={r.V()}"); return self
+    def scale_inplace(self, f): self.log(f"scale {self.V()} f={_f(f)}"); return self
+    def all_reduce_sum_inplace(self): self.log(f"all_reduce {self.V()}"); return self
+    def all_gather_from(self, piece): self.log(f"all_gather dst={self.V()} src={piece.V()}"); return self
+
+    def matmul_vec(self, x):
+        self.log(f"matmul_vec w={self.V()} x={x.V()}")
+        shape = [self.shape()[0]] if len(x.shape()) == 1 else [x.shape()[0], self.shape()[0]]
+        return TraceTensor(TensorStrider(shape), oc.F32, self.device, int(np.prod(shape)))
+
+    def batch_matmul(self, b):
+        self.log(f"batch_matmul a={self.V()} b={b.V()}")
+        shape = [self.shape()[0], self.shape()[1], b.shape()[2]]
+        return TraceTensor(TensorStrider(shape), oc.F32, self.device, int(np.prod(shape)))
+
+
+@pytest.fixture(scope="module")
+def mock_runner(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("mockabi") / "librunner_mock.so")
+    srcs = [os.path.join(ROOT, "crabml_b200", "csrc", "host", "llama2_runner.cpp"), os.path.join(ROOT, "tests", "host", "mock_abi.cpp")]
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", *srcs, "-o", out], check=True, capture_output=True, timeout=300)
+    L = C.CDLL(out)
+    L.mock_device.restype = C.c_void_p
+    L.mock_new_buf.restype, L.mock_new_buf.argtypes = C.c_void_p, [C.c_int, C.c_int64]
+    L.mock_trace_size.restype = C.c_int64
+    L.mock_trace_copy.argtypes = [C.c_char_p]
+    L.ccr_runner_create.argtypes = [C.c_void_p, C.POINTER(capi.ccr_llama_config), C.POINTER(capi.ccr_llama_weights), C.c_int32, C.POINTER(C.c_void_p)]
+    L.ccr_runner_forward.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int64, C.c_void_p]
+    L.ccr_runner_last_error.restype, L.ccr_runner_last_error.argtypes = C.c_char_p, [C.c_void_p]
+    L.ccr_runner_destroy.argtypes = [C.c_void_p]
+    return L
+
+
+def _cpp_trace(L, conf, wt, ct, f16_kv, plan, steps, kv_seq):
+    world = plan.world if plan else 1
+    dim, hd = conf.embedding_dim, conf.embedding_dim // conf.n_heads
+    hid = plan.hidden_local if plan else conf.hidden_dim
+    qd, kvd, vocab_rows = hd * conf.n_heads // world, hd * conf.n_kv_heads // world, conf.vocab_size // world
+    nl = conf.n_layers
+    keep = []
+
+    def arr(dtype, n):
+        a = (C.c_void_p * nl)(*[L.mock_new_buf(dtype, n) for _ in range(nl)])
+        keep.append(a)
+        return C.cast(a, C.POINTER(C.c_void_p))
+    w = capi.ccr_llama_weights(L.mock_new_buf(wt, conf.vocab_size * dim), arr(wt, qd * dim), arr(wt, kvd * dim), arr(wt, kvd * dim),
+                               arr(wt, dim * qd), arr(wt, hid * dim), arr(wt, dim * hid), arr(wt, hid * dim), arr(oc.F32, dim),
+                               arr(oc.F32, dim), L.mock_new_buf(oc.F32, dim), L.mock_new_buf(ct, vocab_rows * dim))
+    cconf = capi.ccr_llama_config(conf.n_heads, conf.n_kv_heads, nl, dim, conf.hidden_dim, conf.seq_len, conf.vocab_size,
+                                  conf.rope_dim or 0, conf.rms_norm_eps, int(f16_kv), plan.rank if plan else 0, world, hid)
+    h = C.c_void_p()
+    L.mock_trace_clear()
+    rc = L.ccr_runner_create(L.mock_device(), C.byref(cconf), C.byref(w), kv_seq, C.byref(h))
+    assert rc == 0
+    logits = np.zeros(conf.vocab_size, np.float32)
+    for pos, tok in steps:
+        t = (C.c_int64 * 1)(tok)
+        rc = L.ccr_runner_forward(h, t, 1, pos, logits.ctypes.data_as(C.c_void_p))
+        assert rc == 0, L.ccr_runner_last_error(h)
+    buf = C.create_string_buffer(int(L.mock_trace_size()) + 1)
+    L.mock_trace_copy(buf)
+    L.ccr_runner_destroy(h)
+    return buf.value.decode().splitlines()
+
+
+def _py_trace(conf, wt, ct, f16_kv, plan, steps, kv_seq):
+    dev = TraceDevice()
+    world = plan.world if plan else 1
+    dim, hd = conf.embedding_dim, conf.embedding_dim // conf.n_heads
+    hid = plan.hidden_local if plan else conf.hidden_dim
+    qd, kvd, vocab_rows = hd * conf.n_heads // world, hd * conf.n_kv_heads // world, conf.vocab_size // world
+    nl = conf.n_layers
+
+    def W(shape, t): return TraceTensor.weight(shape, t, dev)
+    lw = LlamaWeights(token_embed=W([conf.vocab_size, dim], wt), wq=[W([qd, dim], wt) for _ in range(nl)], wk=[W([kvd, dim], wt) for _ in range(nl)],
+                      wv=[W([kvd, dim], wt) for _ in range(nl)], wo=[W([dim, qd], wt) for _ in range(nl)],
+                      ffn_gate_weight=[W([hid, dim], wt) for _ in range(nl)], ffn_down_weight=[W([dim, hid], wt) for _ in range(nl)],
+                      ffn_up_weight=[W([hid, dim], wt) for _ in range(nl)], rms_att_weight=[W([dim], oc.F32) for _ in range(nl)],
+                      rms_ffn_weight=[W([dim], oc.F32) for _ in range(nl)], rms_final_weight=W([dim], oc.F32), output_weight=W([vocab_rows, dim], ct))
+    r = Llama2Runner(TraceTensor, conf, lw, dev, kv_seq, use_f16_kv_cache=f16_kv, world=world)
+    for pos, tok in steps:
+        r.forward([tok], pos)
+    return dev.trace
+
+
+@pytest.mark.parametrize("name,conf,f16_kv,world", [
+    ("tinyllamas", OConf(6, 6, 6, 288, 768, 256, 32000, 1e-5, 48), False, 1),
+    ("llama2-7b-shape", OConf(32, 32, 2, 4096, 11008, 4096, 32000, 1e-5, 128), False, 1),
+    ("gqa-f16kv", OConf(32, 8, 2, 4096, 14336, 4096, 32000, 1e-5, 128), True, 1),
+    ("llama2-7b-sharded-x4", OConf(32, 32, 2, 4096, 11008, 4096, 32000, 1e-5, 128), False, 4),
+])
+def test_cpp_runner_issues_the_reference_op_sequence(mock_runner, name, conf, f16_kv, world):
+    plan = None
+    if world > 1:
+        plan = sharding.make_plan(conf.n_heads, conf.n_kv_heads, conf.embedding_dim, conf.hidden_dim, conf.vocab_size, oc.Q8_0, 1, world, f16_kv)
+    steps = [(0, 1), (1, 365), (2, 2354)]
+    got = _cpp_trace(mock_runner, conf, oc.Q8_0, oc.Q8_0, f16_kv, plan, steps, 16)
+    want = _py_trace(conf, oc.Q8_0, oc.Q8_0, f16_kv, plan, steps, 16)
+    # the KV caches are allocated at construction on both sides; compare everything
+    assert len(got) == len(want), (len(got), len(want), [(a, b) for a, b in zip(got, want) if a != b][:5])
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, f"call {i}: C++ runner `{a}` vs reference replay `{b}`"
+    per_token = (len(got) - 2 * conf.n_layers) // len(steps)
+    assert sum(1 for ln in got if ln.startswith("matmul_vec")) == len(steps) * (7 * conf.n_layers + 1)
+    if world > 1:
+        assert sum(1 for ln in got if ln.startswith("all_reduce")) == len(steps) * 2 * conf.n_layers
+        assert sum(1 for ln in got if ln.startswith("all_gather")) == len(steps)
+    assert per_token > 0
