@@ -20,12 +20,35 @@ static bool view_contiguous(const cc_view* v) {                      // strider.
     return true;
 }
 static bool view_ok(const cc_view* v) { return v && v->buf && v->ndim >= 1 && v->ndim <= CC_MAX_DIMS; }
+// highest element offset the view addresses (-1 for an empty view); negative strides / shapes are rejected by the caller
+static int64_t view_max_offset(const cc_view* v) {
+    int64_t off = 0;
+    for (int i = 0; i < v->ndim; i++) {
+        if (v->shape[i] <= 0) return -1;
+        off += (v->shape[i] - 1) * v->strides[i];
+    }
+    return off;
+}
+static bool view_in_bounds(const cc_view* v) {
+    for (int i = 0; i < v->ndim; i++) if (v->shape[i] < 0 || v->strides[i] < 0) return false;
+    return view_max_offset(v) < v->buf->nelems;
+}
 
+// argument checks shared by every op: a usable view whose highest addressed element lies inside its buffer (the strider lives on
+// the host side of the ABI, so a stale or mismatched shape must become a TensorError here, not an out-of-bounds device read)
 #define CHECK_VIEW(dev, v, what)                                                         \
-    do {                                                                                 \
-        if (!(dev)) return CC_ERR_ARG;                                                   \
-        if (!view_ok(v)) return cc_fail((dev), CC_ERR_ARG, "%s: bad tensor view", what); \
-    } while (0)
+    if (!(dev)) return CC_ERR_ARG;                                                       \
+    CC_ENTER(dev);                                                                       \
+    if (!view_ok(v)) return cc_fail((dev), CC_ERR_ARG, "%s: bad tensor view", what);     \
+    if (!view_in_bounds(v)) return cc_fail((dev), CC_ERR_TENSOR, "%s: view addresses element %lld of a buffer of %lld", what, \
+                                           (long long)view_max_offset(v), (long long)(v)->buf->nelems)
+// a quantized weight matrix is laid out in planes that depend on its row length: the view must be the matrix itself (or a prefix
+// of its rows), never a reshape
+#define CHECK_QUANT_MATRIX(dev, v, what)                                                                                       \
+    if (cc_is_quant((v)->buf->dtype))                                                                                          \
+        CC_REQUIRE(dev, (v)->ndim == 2 && (v)->shape[1] == (v)->buf->cols && (v)->shape[0] <= (v)->buf->rows,                  \
+                   "%s: view [%lld, %lld] does not match the quantized matrix [%lld, %lld]", what, (long long)(v)->shape[0],   \
+                   (long long)((v)->ndim == 2 ? (v)->shape[1] : 0), (long long)(v)->buf->rows, (long long)(v)->buf->cols)
 // lazy mode (lazy.cu): after the same argument checks as eager mode the op is queued instead of launched
 enum { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU, L_ALLREDUCE, L_ALLGATHER };
 int cc_lazy_record(cc_device* dev, int kind, const cc_view* a, const cc_view* b, cc_buf* out, float f, int64_t i0, int64_t i1, int64_t i2,
@@ -65,7 +88,7 @@ extern "C" CC_API int cc_tensor_export_f32(cc_device* dev, const cc_view* src, f
     size_t cnt = n < (size_t)len ? n : (size_t)len;
     if (cnt) CC_CUDA(dev, cudaMemcpyAsync(dst, src->buf->plane[0], cnt * 4, cudaMemcpyDeviceToHost, dev->stream));
     CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
-    return CC_OK;
+    return cc_check_async_error(dev);
 }
 
 extern "C" CC_API int cc_contiguous(cc_device* dev, const cc_view* src, cc_buf** out) {     // cpu_tensor.rs:294-304
@@ -130,6 +153,8 @@ extern "C" CC_API int cc_copy_rows_from(cc_device* dev, const cc_view* dst, cons
     int64_t cols = dst->shape[dst->ndim - 1];
     int be = cc_block_elems(src->buf->dtype);
     CC_REQUIRE(dev, cols % be == 0, "copy_rows_from: row length %lld is not block aligned", (long long)cols);
+    CC_REQUIRE(dev, !cc_is_quant(src->buf->dtype) || cols == src->buf->cols, "copy_rows_from: row length %lld does not match the quantized matrix (%lld columns)",
+               (long long)cols, (long long)src->buf->cols);
     CC_REQUIRE(dev, (int64_t)n_rows * cols <= view_len(dst), "copy_rows_from: dst too small");
     int64_t src_len = view_len(src);
     for (int i = 0; i < n_rows; i++)
@@ -257,6 +282,7 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
     CHECK_VIEW(dev, x, "matmul_vec x");
     if (!out) return cc_fail(dev, CC_ERR_ARG, "matmul_vec: out is NULL");
     CC_REQUIRE(dev, w->ndim == 2, "matmul_vec: weight must be 2d");
+    CHECK_QUANT_MATRIX(dev, w, "matmul_vec");
     CC_REQUIRE(dev, view_contiguous(w) && view_contiguous(x), "matmul_vec: operands must be contiguous");   // matmul_vec.rs:17-18
     CC_REQUIRE(dev, x->ndim == 1 || x->ndim == 2, "matmul_vec: x must be 1d or 2d");
     CC_REQUIRE(dev, w->shape[1] == x->shape[x->ndim - 1], "matmul_vec: last dims differ (%lld vs %lld)",
@@ -337,6 +363,7 @@ extern "C" CC_API int cc_debug_tensor_tap(cc_device* dev, const char* name, cons
     std::vector<float> host((size_t)n);
     if (n) CC_CUDA(dev, cudaMemcpyAsync(host.data(), x->buf->plane[0], (size_t)n * 4, cudaMemcpyDeviceToHost, dev->stream));
     CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
+    { int rc = cc_check_async_error(dev); if (rc) return rc; }
     dev->debug_tensors[name] = std::move(host);
     return CC_OK;
 }

@@ -74,6 +74,7 @@ int cc_comm_world(cc_device* dev) { return dev->comm ? dev->comm->world : 1; }
 
 extern "C" CC_API int cc_comm_create(cc_device* dev, int32_t rank, int32_t world, uint8_t* handle_out /* 64 bytes */) {
     if (!dev || !handle_out) return cc_fail(dev, CC_ERR_ARG, "cc_comm_create: bad argument");
+    CC_ENTER(dev);
     CC_REQUIRE(dev, world >= 1 && world <= CC_COMM_MAX_RANKS && rank >= 0 && rank < world, "comm: rank %d of %d unsupported (max %d ranks)", rank, world, CC_COMM_MAX_RANKS);
     CC_REQUIRE(dev, !dev->comm, "comm: already created on this device");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -93,6 +94,7 @@ extern "C" CC_API int cc_comm_create(cc_device* dev, int32_t rank, int32_t world
 // handles: world x 64 bytes, handles[rank] ignored.  After this call the window of every peer is mapped.
 extern "C" CC_API int cc_comm_connect(cc_device* dev, const uint8_t* handles) {
     if (!dev || !dev->comm || !handles) return cc_fail(dev, CC_ERR_ARG, "cc_comm_connect: create the communicator first");
+    CC_ENTER(dev);
     cc_comm* c = dev->comm;
     for (int p = 0; p < c->world; p++) {
         if (p == c->rank) { c->peer[p] = c->local; continue; }
@@ -124,7 +126,7 @@ extern "C" CC_API int cc_comm_nccl_unique_id(cc_device* dev, uint8_t* id_out /* 
 extern "C" CC_API int cc_comm_init_nccl(cc_device* dev, const uint8_t* id) {
     if (!dev || !dev->comm || !id) return cc_fail(dev, CC_ERR_ARG, "cc_comm_init_nccl: create the communicator first");
     if (!nccl_load(dev)) return CC_ERR_UNSUPPORTED;
-    CC_CUDA(dev, cudaSetDevice(dev->ordinal));
+    CC_ENTER(dev);
     ncclUniqueId uid;
     memcpy(&uid, id, 128);
     int rc = g_nccl.CommInitRank(&dev->comm->nccl, dev->comm->world, uid, dev->comm->rank);

@@ -116,10 +116,28 @@ struct cc_device {
     size_t dev_idx_bytes = 0;
 
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;    // cc_bench_timer_*
+    unsigned* err_host = nullptr;     // host-mapped word a persistent kernel raises when one of its bounded spins times out (mega.cu)
 
     // debug tap
     std::map<std::string, std::vector<float>> debug_tensors;
 };
+
+// Every extern "C" entry point that touches CUDA makes its device current for the duration of the call and restores the caller's
+// afterwards: a cc_device may be driven from any host thread, and one process may own several of them (one per GPU).
+struct CcDeviceGuard {
+    int prev = -1;
+    explicit CcDeviceGuard(const cc_device* dev) {
+        if (!dev) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev->ordinal) { prev = cur; cudaSetDevice(dev->ordinal); }
+    }
+    ~CcDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    CcDeviceGuard(const CcDeviceGuard&) = delete;
+    CcDeviceGuard& operator=(const CcDeviceGuard&) = delete;
+};
+#define CC_CAT2(a, b) a##b
+#define CC_CAT(a, b) CC_CAT2(a, b)
+#define CC_ENTER(dev) CcDeviceGuard CC_CAT(cc_guard_, __LINE__)(dev)
 
 // ---- error plumbing ------------------------------------------------------------------------
 int cc_fail(cc_device* dev, int code, const char* fmt, ...);
@@ -224,7 +242,7 @@ struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; int64_t cols; };
 enum { MK_NORMQ = 0, MK_MATVEC = 1, MK_ATTN = 2, MK_ROWS = 3, MK_REDUCE = 4, MK_GATHER = 5 };
 struct MkPhase {
     int type, wtype, write_back, next_matvec;
-    int xgpu, red_n; float* red_dst; const float* red_res;   // cross-GPU barrier after this phase ; REDUCE/GATHER phase operands   // next_matvec: index of the next MATVEC phase (look-ahead prefetch), -1 if none
+    int xgpu, red_n, next_matvec2, spare; float* red_dst; const float* red_res;   // cross-GPU barrier after this phase ; REDUCE/GATHER phase operands   // next_matvec / next_matvec2: index of the next MATVEC phase and of the one after it (look-ahead prefetch), -1 if none
     // NORMQ (and the output quantisation of ATTN)
     float* x; float* orig; const float* norm_w; float eps; int n; ActQ8_0 act;
     StreamArgs mv;                      // MATVEC
@@ -232,7 +250,7 @@ struct MkPhase {
     unsigned long long dyn_off, rope_off;   // ATTN {pos, kv_len} / ROWS row list ; RoPE table
     DeqPlanes planes; int src_dtype, dst_dtype, n_rows, pad; long long cols; void* dst;   // ROWS
 };
-size_t cc_mega_smem_for_phase(const MkPhase& ph);
+size_t cc_mega_smem_for_phase(const MkPhase& ph);      // working area, without the norm-weight staging area on top of it
 const CommDev* cc_comm_dev(cc_device* dev);
 bool cc_comm_is_nccl(cc_device* dev);
 int cc_comm_world(cc_device* dev);
@@ -240,7 +258,9 @@ void cc_comm_destroy(cc_device* dev);
 int cc_launch_all_reduce(cc_device* dev, float* x, int64_t n, const float* residual);
 int cc_launch_all_gather(cc_device* dev, const float* src, int64_t n, float* dst);
 extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase);
-int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof, const CommDev* comm);
+int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem_work, size_t smem_wstage,
+                   unsigned long long* prof, const CommDev* comm);
+int cc_check_async_error(cc_device* dev);     // after a stream synchronize: did a persistent kernel give up on a barrier?
 int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch, bool write_back);
 int cc_launch_attn_decode(cc_device* dev, const AttnArgs& a);
 struct LazyState;
@@ -278,6 +298,36 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// ---- canonical reduction orders ---------------------------------------------------------------------------------
+// Every execution mode (eager ops.cu, fused kernels of the CUDA-graph mode, phases of the megakernel) reduces a row with
+// the SAME grouping, so the three modes are bit-identical to each other (tests/test_gpu_runner.py):
+//   a CTA of CC_RED_THREADS = 512 threads; thread t accumulates the items t, t + 512, t + 1024, ... in that order
+//   (for sums of squares an item is a float4 chunk: ss += x*x + y*y + z*z + w*w, left to right), then the xor-butterfly
+//   warp_sum, then the 16 warp sums are added in warp order 0..15 by every thread.
+#define CC_RED_THREADS 512
+#define CC_RED_WARPS 16
+__device__ __forceinline__ float cc_block_sum_512(float v, float* s_red /* [16] */) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < CC_RED_WARPS; w++) t += s_red[w];
+    __syncthreads();                       // s_red may be reused by the caller
+    return t;
+}
+__device__ __forceinline__ float cc_block_max_512(float v, float* s_red /* [16] */) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = s_red[0];
+#pragma unroll
+    for (int w = 1; w < CC_RED_WARPS; w++) t = fmaxf(t, s_red[w]);
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ float cc_sq4(const float4& v) { return v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+
 // streaming 128-bit load of weight data: read exactly once per token, keep it out of L1
 __device__ __forceinline__ int4 ld_stream_16(const void* p) {
     int4 r;

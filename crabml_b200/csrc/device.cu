@@ -106,6 +106,7 @@ extern "C" CC_API void cc_device_destroy(cc_device* dev) {
         for (uintptr_t p : kv.second) cudaFree((void*)p);
     if (dev->act_scratch) cudaFree(dev->act_scratch);
     if (dev->pinned) cudaFreeHost(dev->pinned);
+    if (dev->err_host) cudaFreeHost(dev->err_host);
     if (dev->dev_idx) cudaFree(dev->dev_idx);
     cudaFree(dev->exp_lut);
     cudaFree(dev->gelu_lut);
@@ -119,17 +120,20 @@ extern "C" CC_API void* cc_device_stream(cc_device* dev) { return dev ? (void*)d
 
 extern "C" CC_API int cc_device_synchronize(cc_device* dev) {
     if (!dev) return CC_ERR_ARG;
+    CC_ENTER(dev);
     if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
-    return CC_OK;
+    return cc_check_async_error(dev);
 }
 extern "C" CC_API int cc_device_flush(cc_device* dev) {
     if (!dev) return CC_ERR_ARG;
+    CC_ENTER(dev);
     return dev->lz ? cc_lazy_flush(dev) : CC_OK;
 }
 
 extern "C" CC_API int cc_bench_timer_begin(cc_device* dev) {
     if (!dev) return CC_ERR_ARG;
+    CC_ENTER(dev);
     if (!dev->ev_begin) { CC_CUDA(dev, cudaEventCreate(&dev->ev_begin)); CC_CUDA(dev, cudaEventCreate(&dev->ev_end)); }
     if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_CUDA(dev, cudaEventRecord(dev->ev_begin, dev->stream));
@@ -137,11 +141,12 @@ extern "C" CC_API int cc_bench_timer_begin(cc_device* dev) {
 }
 extern "C" CC_API int cc_bench_timer_end(cc_device* dev, float* ms) {
     if (!dev || !ms || !dev->ev_begin) return CC_ERR_ARG;
+    CC_ENTER(dev);
     if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_CUDA(dev, cudaEventRecord(dev->ev_end, dev->stream));
     CC_CUDA(dev, cudaEventSynchronize(dev->ev_end));
     CC_CUDA(dev, cudaEventElapsedTime(ms, dev->ev_begin, dev->ev_end));
-    return CC_OK;
+    return cc_check_async_error(dev);
 }
 
 // ---- activation pool: power-of-two size classes, stream-ordered reuse (single stream) -------------
@@ -220,8 +225,9 @@ extern "C" CC_API void cc_tensor_retain(cc_buf* b) { if (b) b->refs.fetch_add(1)
 extern "C" CC_API void cc_tensor_release(cc_buf* b) {
     if (!b) return;
     if (b->refs.fetch_sub(1) != 1) return;
+    CC_ENTER(b->dev);
     if (b->pooled) cc_pool_free(b->dev, b->base, b->bytes);
-    else if (b->base) { cudaSetDevice(b->dev->ordinal); cudaFree(b->base); }
+    else if (b->base) cudaFree(b->base);
     if (b->raw) cudaFree(b->raw);
     delete b;
 }
@@ -236,6 +242,7 @@ static int64_t prod(const int64_t* shape, int ndim) {
 
 extern "C" CC_API int cc_tensor_alloc(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t t, cc_buf** out) {
     if (!dev || !shape || !out || ndim < 1 || ndim > CC_MAX_DIMS) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_alloc: bad argument");
+    CC_ENTER(dev);
     CC_REQUIRE(dev, t == CC_F32 || t == CC_F16, "only f32/f16 is supported");   // cpu_tensor.rs:139-141
     // F32 is zero-filled (vec![0.0; n]); F16 is uninitialised in the reference (buf_f16.rs:23-28), zeroed here
     return cc_new_activation(dev, prod(shape, ndim), t, true, out);
@@ -244,6 +251,7 @@ extern "C" CC_API int cc_tensor_alloc(cc_device* dev, const int64_t* shape, int3
 extern "C" CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size_t nbytes, const int64_t* shape,
                                   int32_t ndim, int32_t t, cc_buf** out) {
     if (!dev || !bytes || !shape || !out || ndim < 1 || ndim > CC_MAX_DIMS) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_from_cpu: bad argument");
+    CC_ENTER(dev);
     int be = cc_block_elems(t);
     CC_REQUIRE(dev, be > 0, "from_cpu: unsupported ggml type %d", t);
     int64_t n = prod(shape, ndim);
@@ -289,6 +297,7 @@ extern "C" CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size
 extern "C" CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t t, uint64_t seed,
                                uint64_t tensor_id, float scale, cc_buf** out) {
     if (!dev || !shape || !out || ndim < 1 || ndim > CC_MAX_DIMS) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_synth: bad argument");
+    CC_ENTER(dev);
     int be = cc_block_elems(t);
     CC_REQUIRE(dev, be > 1, "synth: quantized types only, got %d", t);
     int64_t n = prod(shape, ndim);
@@ -322,6 +331,7 @@ extern "C" CC_API int cc_tensor_synth(cc_device* dev, const int64_t* shape, int3
 extern "C" CC_API int cc_tensor_synth_slice(cc_device* dev, const int64_t* shape, int32_t ndim, int32_t t, uint64_t seed, uint64_t tensor_id,
                                             float scale, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, cc_buf** out) {
     if (!dev || !shape || !out || ndim != 2) return cc_fail(dev, CC_ERR_ARG, "cc_tensor_synth_slice: bad argument (2-d tensors only)");
+    CC_ENTER(dev);
     int be = cc_block_elems(t);
     CC_REQUIRE(dev, be > 1, "synth_slice: quantized types only, got %d", t);
     const int64_t rows = shape[0], cols = shape[1];
@@ -361,6 +371,7 @@ extern "C" CC_API int cc_tensor_synth_slice(cc_device* dev, const int64_t* shape
 
 extern "C" CC_API int cc_test_export_blocks(cc_device* dev, const cc_buf* buf, void* dst, size_t nbytes) {
     if (!dev || !buf || !dst) return cc_fail(dev, CC_ERR_ARG, "cc_test_export_blocks: bad argument");
+    CC_ENTER(dev);
     if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_REQUIRE(dev, cc_is_quant(buf->dtype), "export_blocks: not a quantized tensor");
     size_t need = (size_t)(buf->nelems / cc_block_elems(buf->dtype)) * cc_block_bytes(buf->dtype);

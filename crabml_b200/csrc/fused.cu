@@ -14,7 +14,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 //   x <- (x / sqrt(sum(x^2)/n + eps)) * w   (optional)      rms_norm_inplace + mul_inplace (rms_norm.rs:32-47, llama2.rs:231-232,611-612)
 //   act <- quantize_q8_0(x)                                 buf_q8_0.rs:87-134 (what matmul_vec does first, matmul_vec.rs:37-40)
 // ---------------------------------------------------------------------------------------------------------------
-#define NQ_THREADS 256
+#define NQ_THREADS CC_RED_THREADS            // canonical reduction order (common.cuh)
 #define NQ_MAX_CTAS 16
 // Every CTA recomputes sum(x^2) over the whole row (a few KB from L2, same order in every CTA -> identical rms), then
 // normalises / copies / quantises only its own slice of 32-element blocks.
@@ -35,15 +35,9 @@ __global__ void __launch_bounds__(NQ_THREADS) normq_kernel(float* x, float* orig
 #pragma unroll
             for (int j = 0; j < 4; j++) { int i = i0 + j * NQ_THREADS + threadIdx.x; v[j] = i < n4 ? x4[i] : make_float4(0, 0, 0, 0); }
 #pragma unroll
-            for (int j = 0; j < 4; j++) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+            for (int j = 0; j < 4; j++) ss += cc_sq4(v[j]);
         }
-        ss = warp_sum(ss);
-        if (lane == 0) s_red[warp] = ss;
-        __syncthreads();
-        float t = 0.0f;
-#pragma unroll
-        for (int w = 0; w < NQ_THREADS / 32; w++) t += s_red[w];
-        rms = sqrtf(t / (float)n + eps);
+        rms = sqrtf(cc_block_sum_512(ss, s_red) / (float)n + eps);
     }
     const int nb = n >> 5;
     const int gw = blockIdx.x * (NQ_THREADS / 32) + warp, tw = gridDim.x * (NQ_THREADS / 32);
@@ -71,7 +65,7 @@ __global__ void __launch_bounds__(NQ_THREADS) normq_kernel(float* x, float* orig
 // and additionally emits the Q8_0 quantisation of the output row (input of wo.matmul_vec).
 // dyn: {pos, kv_len}; rope_tab: cos[pairs] then sin[pairs].
 // ---------------------------------------------------------------------------------------------------------------
-#define AT_THREADS 128
+#define AT_THREADS CC_RED_THREADS            // canonical softmax order (common.cuh); also 16 score warps per head
 template <bool KV_F16>
 __global__ void __launch_bounds__(AT_THREADS) attn_decode_kernel(const float* __restrict__ q_in, const float* __restrict__ k_in, const float* __restrict__ v_in,
                                                                  void* kcache, void* vcache, float* __restrict__ out, ActQ8_0 act,

@@ -84,6 +84,12 @@ public:
     ~CudaTensor() { if (buf_) cc_tensor_release(buf_); }
 
     static CudaTensor wrap(cc_device* dev, cc_buf* borrowed, const std::vector<int64_t>& shape) {   // weights owned elsewhere
+        if (!borrowed) throw TensorError("wrap: null tensor");
+        int64_t n = 1;
+        for (int64_t d : shape) n *= d;
+        // a weight handed over with the wrong shape (config / file mismatch) must be a TensorError here, not a silent misread
+        if (n != cc_tensor_capacity(borrowed))
+            throw TensorError("wrap: shape has " + std::to_string(n) + " elements, the tensor holds " + std::to_string(cc_tensor_capacity(borrowed)));
         cc_tensor_retain(borrowed);
         return CudaTensor(dev, borrowed, TensorStrider(shape));
     }

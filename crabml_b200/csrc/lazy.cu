@@ -35,7 +35,11 @@ struct LOp {
     bool done = false;
 };
 
-struct GraphEntry { cudaGraphExec_t exec = nullptr; size_t dyn_bytes = 0; uint64_t launches = 0; MkPhase* phases_dev = nullptr; };
+// one captured token graph.  The cache key is a 64-bit fold of the launch signature; `sig` is the signature itself and is compared
+// on every hit (a colliding key must re-capture, never replay another plan's baked pointers); `last_use` drives the LRU bound.
+struct GraphEntry { cudaGraphExec_t exec = nullptr; size_t dyn_bytes = 0; uint64_t launches = 0; MkPhase* phases_dev = nullptr;
+                    std::vector<uint64_t> sig; uint64_t last_use = 0; };
+#define LZ_MAX_GRAPHS 64                             // cached token graphs per device (a decode loop needs 2-4)
 
 struct LazyState {
     std::vector<LOp> q;
@@ -52,7 +56,7 @@ struct LazyState {
     std::vector<int> prof_types;
     size_t act_cap = 0;
     std::unordered_map<uint64_t, GraphEntry> cache;
-    uint64_t flushes = 0, graph_hits = 0, captures = 0, uncached = 0;
+    uint64_t flushes = 0, graph_hits = 0, captures = 0, uncached = 0, evictions = 0, collisions = 0;
     uint64_t ns_record = 0, ns_fuse = 0, ns_submit = 0, n_ops = 0;      // host-side cost accounting
 };
 
@@ -72,6 +76,17 @@ static bool vcontig(const LView& v) {
     return true;
 }
 
+static void graph_entry_free(GraphEntry& ge) {
+    if (ge.exec) cudaGraphExecDestroy(ge.exec);
+    if (ge.phases_dev) cudaFree(ge.phases_dev);
+    ge.exec = nullptr; ge.phases_dev = nullptr;
+}
+// drop every cached graph (their baked pointers are stale after the scratch buffers moved); the stream must be idle
+static void graph_cache_clear(LazyState* lz) {
+    for (auto& kv : lz->cache) graph_entry_free(kv.second);
+    lz->cache.clear();
+}
+
 LazyState* cc_lazy_create(cc_device* dev) {
     LazyState* lz = new LazyState();
     for (int i = 0; i < LZ_DYN_SLOTS; i++)
@@ -79,13 +94,18 @@ LazyState* cc_lazy_create(cc_device* dev) {
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
     if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 4 * 4096);
     if (cudaMalloc(&lz->bar_dev, 4096) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 4096) != cudaSuccess) { delete lz; return nullptr; }
+    if (!dev->err_host) {
+        if (cudaHostAlloc((void**)&dev->err_host, 64, cudaHostAllocMapped) != cudaSuccess) { delete lz; return nullptr; }
+        *dev->err_host = 0u;
+    }
     return lz;
 }
 void cc_lazy_destroy(cc_device* dev) {
     LazyState* lz = dev->lz;
     if (!lz) return;
     for (auto& op : lz->q) { if (op.a.buf) cc_tensor_release(op.a.buf); if (op.b.buf) cc_tensor_release(op.b.buf); if (op.out) cc_tensor_release(op.out); }
-    for (auto& kv : lz->cache) { cudaGraphExecDestroy(kv.second.exec); if (kv.second.phases_dev) cudaFree(kv.second.phases_dev); }
+    for (auto& kv : lz->cache) graph_entry_free(kv.second);
+    lz->cache.clear();
     if (lz->bar_dev) cudaFree(lz->bar_dev);
     for (int i = 0; i < LZ_DYN_SLOTS; i++) { if (lz->dyn_host[i]) cudaFreeHost(lz->dyn_host[i]); if (lz->dyn_ev[i]) cudaEventDestroy(lz->dyn_ev[i]); }
     if (lz->dyn_dev) cudaFree(lz->dyn_dev);
@@ -119,7 +139,7 @@ struct Plan {
     bool cacheable = true;
     std::vector<MkPhase> phases;     // megakernel form of the same plan (valid while mega_ok)
     bool mega_ok = true;
-    size_t mega_smem = 1024;
+    size_t mega_smem = 1024, mega_wstage = 0;
     void S(uint64_t v) { sig.push_back(v); }
     void SP(const void* p) { sig.push_back((uint64_t)(uintptr_t)p); }
     size_t dyn_put(const void* p, size_t n) {
@@ -477,11 +497,14 @@ int cc_lazy_flush(cc_device* dev) {
     // scratch for the quantised activations (largest k in the queue)
     int64_t max_k = 0;
     for (auto& op : lz->q) if (op.kind == L_MATVEC) max_k = std::max<int64_t>(max_k, std::max<int64_t>(op.a.shape[1], 0));
-    for (auto& op : lz->q) if (op.kind == L_BMM) max_k = std::max<int64_t>(max_k, op.a.shape[0] * op.b.shape[2]);
+    // the fused attention quantises its OUTPUT row (n_heads * head_dim = the PV product's a_batch * n) into act[1]; QK^T products
+    // ([heads, 1, kv_len + 1]) are never quantised, so the scratch does not grow with the context
+    for (auto& op : lz->q) if (op.kind == L_BMM && op.b.ndim == 3 && op.b.strides[2] == 1) max_k = std::max<int64_t>(max_k, op.a.shape[0] * op.b.shape[2]);
     size_t need = cc_act_bytes(CC_Q8_0, (max_k + 255) / 256 * 256) + 256;
     int rc = CC_OK;
     if (need > lz->act_cap) {
         cudaStreamSynchronize(dev->stream);
+        graph_cache_clear(lz);                       // cached graphs hold the old scratch pointers
         for (int i = 0; i < 2; i++) { if (lz->act[i]) cudaFree(lz->act[i]); lz->act[i] = nullptr; }
         size_t cap = 4096; while (cap < need) cap <<= 1;
         for (int i = 0; i < 2; i++) if (cudaMalloc(&lz->act[i], cap) != cudaSuccess) return cc_fail(dev, CC_ERR_CUDA, "lazy: scratch alloc failed");
@@ -523,6 +546,21 @@ int cc_lazy_flush(cc_device* dev) {
         P.S(P.dyn.size());
         uint64_t key = hash_sig(P.sig);
         auto it = lz->cache.find(key);
+        if (it != lz->cache.end() && it->second.sig != P.sig) {          // 64-bit key collision: never replay the other plan's graph
+            lz->collisions++;
+            cudaStreamSynchronize(dev->stream);
+            graph_entry_free(it->second);
+            lz->cache.erase(it);
+            it = lz->cache.end();
+        }
+        if (it == lz->cache.end() && lz->cache.size() >= LZ_MAX_GRAPHS) {   // LRU bound: evict the entry replayed longest ago
+            auto victim = lz->cache.begin();
+            for (auto c = lz->cache.begin(); c != lz->cache.end(); ++c) if (c->second.last_use < victim->second.last_use) victim = c;
+            cudaStreamSynchronize(dev->stream);          // its last launch may still be running
+            graph_entry_free(victim->second);
+            lz->cache.erase(victim);
+            lz->evictions++;
+        }
         if (it == lz->cache.end()) {
             lz->captures++;
             uint64_t l0 = dev->launches;
@@ -530,9 +568,15 @@ int cc_lazy_flush(cc_device* dev) {
             GraphEntry ge;
             const bool use_mega = dev->mega && P.mega_ok && !P.phases.empty();
             if (use_mega) {       // phase table lives in device memory for the lifetime of the graph
-                int nxt = -1;
-                for (int t = (int)P.phases.size() - 1; t >= 0; t--) { P.phases[t].next_matvec = nxt; if (P.phases[t].type == MK_MATVEC) nxt = t; }
-                for (auto& ph : P.phases) P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_phase(ph));
+                int nxt = -1, nxt2 = -1;
+                for (int t = (int)P.phases.size() - 1; t >= 0; t--) {
+                    P.phases[t].next_matvec = nxt; P.phases[t].next_matvec2 = nxt2;
+                    if (P.phases[t].type == MK_MATVEC) { nxt2 = nxt; nxt = t; }
+                }
+                for (auto& ph : P.phases) {
+                    P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_phase(ph));
+                    if (ph.type == MK_MATVEC && ph.x && ph.norm_w) P.mega_wstage = std::max(P.mega_wstage, (size_t)ph.n * 4);
+                }
                 if (cudaMalloc(&ge.phases_dev, P.phases.size() * sizeof(MkPhase)) != cudaSuccess ||
                     cudaMemcpy(ge.phases_dev, P.phases.data(), P.phases.size() * sizeof(MkPhase), cudaMemcpyHostToDevice) != cudaSuccess)
                     rc = cc_fail(dev, CC_ERR_CUDA, "lazy: phase table upload failed");
@@ -541,7 +585,7 @@ int cc_lazy_flush(cc_device* dev) {
             if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
             if (!rc) {
                 if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue : 0)); }
-                rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem,
+                rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem, P.mega_wstage,
                                                P.phases.size() < 4000 ? lz->prof_dev : nullptr, cc_comm_dev(dev)) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);
                 if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: end capture: %s", cudaGetErrorString(e));
@@ -553,6 +597,7 @@ int cc_lazy_flush(cc_device* dev) {
             if (graph) cudaGraphDestroy(graph);
             if (!rc) {
                 ge.dyn_bytes = P.dyn.size();
+                ge.sig = P.sig;
                 ge.launches = dev->launches - l0;
                 dev->launches = l0;            // counted when the graph is launched
                 it = lz->cache.emplace(key, ge).first;
@@ -561,6 +606,7 @@ int cc_lazy_flush(cc_device* dev) {
             lz->graph_hits++;
         }
         if (!rc) {
+            it->second.last_use = lz->flushes;
             cudaError_t e = cudaGraphLaunch(it->second.exec, dev->stream);
             if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: graph launch: %s", cudaGetErrorString(e));
             else dev->launches += it->second.launches;
@@ -578,6 +624,18 @@ int cc_lazy_flush(cc_device* dev) {
         if (op.a.buf) cc_tensor_release(op.a.buf);
     }
     return rc;
+}
+
+// Called after a stream synchronize.  A persistent kernel that gave up on a barrier (MkSpin in mega.cu) has raised the host-mapped
+// error word: report it, and reset the barrier words (their monotonic counters are inconsistent after a drained launch).
+int cc_check_async_error(cc_device* dev) {
+    if (!dev || !dev->err_host) return CC_OK;
+    const unsigned code = *(volatile unsigned*)dev->err_host;
+    if (!code) return CC_OK;
+    *(volatile unsigned*)dev->err_host = 0u;
+    if (dev->lz && dev->lz->bar_dev) cudaMemset(dev->lz->bar_dev, 0, 4096);
+    return cc_fail(dev, CC_ERR_CUDA, "megakernel barrier timeout (%s): the grid was not co-resident or a peer GPU stopped responding",
+                   code == 2u ? "cross-GPU handshake" : "grid barrier");
 }
 
 // developer profiling: per-phase start timestamps (ns) of the last megakernel run + phase type codes

@@ -44,6 +44,30 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm vo
 // replay needs no reset node in front of the kernel.
 __device__ __forceinline__ void red_add_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 #define MK_BAR_THREAD (MK_THREADS - 1)
+#define MK_BAR_ERR 64                        // bar[64]: non-zero once any spin on this GPU has timed out
+#define MK_SPIN_CHECK 0x7FFFu                // iterations between two looks at the clock / the error word
+#define MK_SPIN_TIMEOUT_NS 4000000000ull     // a healthy barrier takes microseconds
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Every spin is bounded: after MK_SPIN_TIMEOUT_NS without progress (a CTA that never became resident because another tenant holds
+// an SM, a peer GPU that died) the waiter raises the error word -- device copy for the other spinners, host-mapped copy for
+// cc_synchronize / cc_lazy_flush, which report CC_ERR_CUDA "megakernel barrier timeout" -- and the kernel drains.
+struct MkSpin {
+    unsigned it = 0; unsigned long long t0 = 0;
+    __device__ __forceinline__ bool expired(unsigned* bar, unsigned* err_host, unsigned code) {
+        if ((++it & MK_SPIN_CHECK) != 0) return false;
+        if (*(volatile unsigned*)&bar[MK_BAR_ERR]) return true;
+        const unsigned long long t = globaltimer_ns();
+        if (!t0) { t0 = t; return false; }
+        if (t - t0 < MK_SPIN_TIMEOUT_NS) return false;
+        atomicExch(&bar[MK_BAR_ERR], code);
+        if (err_host) { *(volatile unsigned*)err_host = code; __threadfence_system(); }
+        return true;
+    }
+};
 __device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen, bool xgpu = false) {
     __syncthreads();
     if (threadIdx.x == MK_BAR_THREAD) {
@@ -54,33 +78,36 @@ __device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblo
 // xseq != 0: the barrier doubles as the handshake of exchange number xseq with the other GPUs (protocol: comm.cu).  CTA 0's
 // barrier thread, once every local CTA has arrived (all partial rows are stored in the peers' slots), publishes xseq in each
 // peer's flag word, waits for every peer's xseq in its own flag words, and only then opens the local barrier.
-__device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblocks, unsigned gen, const CommDev& comm, unsigned xseq = 0) {
+// poll_counter: (local barriers only) every CTA watches the arrival counter itself -- one L2 round trip less than
+// counter -> CTA 0 -> generation word; CTA 0 still publishes the generation (the next launch starts from it).
+__device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblocks, unsigned gen, const CommDev& comm, unsigned xseq, bool poll_counter,
+                                                  int* s_abort, unsigned* err_host) {
     const int lane = threadIdx.x & 31;
     if ((threadIdx.x >> 5) == MK_WARPS - 1) {              // the warp of MK_BAR_THREAD (its lane 31)
+        const unsigned target = (gen + 1u) * nblocks;
+        bool ok = true;
         if (blockIdx.x == 0) {
-            if (lane == 31) { const unsigned target = (gen + 1u) * nblocks; while (ld_acquire_u32(&bar[0]) != target) { } }
+            if (lane == 31) { MkSpin sp; while (ld_acquire_u32(&bar[0]) != target) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }
             if (xseq) {                                     // kernel-uniform: the whole warp takes this branch together
                 __syncwarp();                               // every local CTA has arrived: all partial rows are in the peers' slots
                 if (lane < comm.world) {                    // one lane per peer: publish and poll in parallel, not rank after rank
                     __threadfence_system();
                     cc_st_release_sys(comm.flag[lane] + comm.rank * 32, xseq);
                     const unsigned* f = comm.flag[comm.rank] + lane * 32;
-                    while ((int)(cc_ld_acquire_sys(f) - xseq) < 0) { }
+                    MkSpin sp;
+                    while ((int)(cc_ld_acquire_sys(f) - xseq) < 0) if (sp.expired(bar, err_host, 2u)) { ok = false; break; }
                 }
                 __syncwarp();
             }
             if (lane == 31) st_release_u32(&bar[32], gen + 1u);
         } else if (lane == 31) {
-            while (ld_acquire_u32(&bar[32]) != gen + 1u) { }
+            MkSpin sp;
+            if (poll_counter && !xseq) { while (ld_acquire_u32(&bar[0]) != target) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }
+            else { while (ld_acquire_u32(&bar[32]) != gen + 1u) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }
         }
+        if (!ok) *s_abort = 1;
     }
     __syncthreads();
-}
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
 }
 
 __device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
@@ -185,22 +212,6 @@ __device__ __forceinline__ float mk_seg_dot(const MkSeg& S, int seg, const int4*
     return acc;
 }
 
-// ---- TMA-staged segments: two more segments per warp wait in shared memory ----------------------------------------------------
-// A segment of a row is ONE contiguous run of bytes in the quant plane (MK_SEG groups x 1 KB for Q8_0, 512 B for Q4_0), so it
-// is fetched with a single cp.async.bulk (TMA, no registers, no LSU instructions) that signals a per-(warp, stage) mbarrier.
-// Together with the two register-resident segments a warp keeps 4 segments = 17 KB in flight, 41 MB per GPU: enough to cover
-// the grid barrier AND the activation prologue of the next phase with streaming.
-#define MK_STAGES 2
-#ifndef MK_DEEP
-#define MK_DEEP 0
-#endif
-#define MK_STAGE_BYTES 4096
-#define MK_STAGING (MK_WARPS * MK_STAGES * MK_STAGE_BYTES)     // 128 KB at the bottom of dynamic shared memory
-struct MkPipe {
-    MkSeg buf0, buf1;                    // register stages (segments u % 4 == 0, 1)
-    uint16_t sc0[MK_SEG], sc1[MK_SEG];   // f16 scales of the two TMA stages (segments u % 4 == 2, 3)
-    unsigned par;                        // bit s = parity the next wait on stage s must see
-};
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
     asm volatile(
@@ -208,44 +219,13 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@!p bra MK_WAIT_%=;\n}\n" ::"r"(mbar), "r"(parity) : "memory");
 }
-template <int TYPE>
-__device__ __forceinline__ void mk_stage_issue(unsigned stage_smem, unsigned mbar, uint16_t (&sc)[MK_SEG], const MkRowPtr& p, int seg, int nb, int lane, bool valid) {
-    constexpr int GB = TYPE == CC_Q8_0 ? 1024 : 512;
-    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
-    if (valid && lane == 0) {
-        const unsigned off = (unsigned)seg * (MK_SEG * GB);
-        unsigned bytes = (unsigned)nb * BB - off;
-        if (bytes > MK_SEG * GB) bytes = MK_SEG * GB;
-        const uint8_t* src = p.q + off;                    // lane 0: p.q is the row base
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-    }
-    const uint16_t* d = p.d + seg * (MK_SEG * 32);
-#pragma unroll
-    for (int g = 0; g < MK_SEG; g++) sc[g] = valid && ((seg * MK_SEG + g) * 32 + lane < nb) ? d[g * 32] : (uint16_t)0;
-}
-// lanes beyond the row (or groups beyond it) carry scale 0, so whatever bytes the stage holds there contribute exactly 0
-template <int TYPE>
-__device__ __forceinline__ float mk_stage_dot(const int4* st, const uint16_t (&sc)[MK_SEG], int seg, int GR, int last_half_off, int lane, const int4* aq_l, const float* ad_l, const int* as_l) {
-    float acc = 0.0f;
-    const int4* aq = aq_l + seg * (MK_SEG * 64);
-    const float* ad = ad_l + seg * (MK_SEG * 32);
-#pragma unroll
-    for (int g = 0; g < MK_SEG; g++) {
-        if constexpr (TYPE == CC_Q8_0) {
-            const int hoff = (seg * MK_SEG + g == GR - 1 ? last_half_off : 512) >> 4;
-            const int4 wa = st[g * 64 + lane], wb = st[g * 64 + hoff + lane];
-            int sumi = mk_dp16(wa, aq[g * 64]) + mk_dp16(wb, aq[g * 64 + 1]);
-            acc += (float)sumi * h2f_bits(sc[g]) * ad[g * 32];
-        } else {
-            const int4 w = st[g * 32 + lane];
-            int4 lo = make_int4(w.x & 0x0F0F0F0F, w.y & 0x0F0F0F0F, w.z & 0x0F0F0F0F, w.w & 0x0F0F0F0F);
-            int4 hi = make_int4((w.x >> 4) & 0x0F0F0F0F, (w.y >> 4) & 0x0F0F0F0F, (w.z >> 4) & 0x0F0F0F0F, (w.w >> 4) & 0x0F0F0F0F);
-            int sumi = mk_dp16(lo, aq[g * 64]) + mk_dp16(hi, aq[g * 64 + 1]) - 8 * as_l[(seg * MK_SEG + g) * 32];
-            acc += (float)sumi * h2f_bits(sc[g]) * ad[g * 32];
-        }
-    }
-    return acc;
+struct MkPipe { MkSeg buf0, buf1; };      // register stages of the weight stream, live across phases and barriers
+
+// L2 look-ahead: cp.async.bulk.prefetch.L2 (TMA, fire-and-forget, no registers, no shared memory) pulls whole weight rows into
+// the 126 MB L2 long before the warp that owns them issues its register loads -- across barriers, prologues and small phases --
+// so HBM keeps streaming while the grid synchronises.  src 16-byte aligned, size a multiple of 16.
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 // geometry of one MATVEC phase for this warp
@@ -285,26 +265,56 @@ __device__ __forceinline__ MkRowPtr mk_vrow_ptr(const StreamMats& M, const MkGeo
     return p;
 }
 
-// Issue the loads of this warp's first two (deep: four) segments of a MATVEC phase.  Weights are immutable, so this may run
-// long before the phase itself -- across barriers and small phases -- keeping HBM busy while the grid synchronises.
+// L2 prefetch of the virtual rows [i0, i1) of this warp's row list (clipped to the list): lane j takes row i0 + j, one bulk
+// request for the row's quants and one for its f16 scales (skipped when the scale row is not a multiple of 16 bytes).
 template <int TYPE>
-__device__ __forceinline__ void matvec_prefetch(const StreamArgs& A, MkPipe& P, bool deep, unsigned stage0_smem, unsigned mbar0) {
+__device__ __forceinline__ void mk_l2_rows(const StreamArgs& A, const MkGeo& g, int i0, int i1) {
+    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
+    const int nv = g.U / g.NSEG;
+    const int i = i0 + (int)(threadIdx.x & 31);
+    if (i < i1 && i < nv) {
+        const MkRowPtr p = mk_vrow_ptr<TYPE>(A.mats, g, i, 0);
+        l2_prefetch(p.q, (unsigned)(g.nb * BB));
+        if (((g.nb * 2) & 15) == 0) l2_prefetch(p.d, (unsigned)(g.nb * 2));
+    }
+}
+// first virtual row the L2 look-ahead has to cover: the register stages hold segments 0 and 1
+__device__ __forceinline__ int mk_l2_first_row(const MkGeo& g) { return 2 / g.NSEG; }
+// rows of L2 look-ahead a byte budget buys for this phase (at least 1)
+template <int TYPE>
+__device__ __forceinline__ int mk_l2_depth(const MkGeo& g, int budget_bytes) {
+    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
+    const int d = budget_bytes / (g.nb * BB);
+    return d < 1 ? 1 : (d > 31 ? 31 : d);
+}
+
+// Issue the loads of this warp's first two segments of a MATVEC phase (register stages) and, with an L2 budget, the bulk L2
+// prefetch of the rows behind them.  Weights are immutable, so this may run long before the phase itself -- across barriers
+// and small phases -- keeping HBM busy while the grid synchronises.  Returns the bytes of this warp's share of the phase.
+template <int TYPE>
+__device__ __forceinline__ int matvec_prefetch(const StreamArgs& A, MkPipe& P, int l2_budget) {
+    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
     const int lane = threadIdx.x & 31;
     const MkGeo g = mk_geo(A);
     int l_i = 0, l_seg = 0;
     MkRowPtr l_ptr = mk_vrow_ptr<TYPE>(A.mats, g, 0, lane);
     auto advance_load = [&]() { if (++l_seg == g.NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(A.mats, g, ++l_i, lane); } };
     mk_seg_load<TYPE>(P.buf0, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 0); advance_load();
-    mk_seg_load<TYPE>(P.buf1, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 1); advance_load();
-    if (deep) {
-        mk_stage_issue<TYPE>(stage0_smem, mbar0, P.sc0, l_ptr, l_seg, g.nb, lane, g.U > 2); advance_load();
-        mk_stage_issue<TYPE>(stage0_smem + MK_STAGE_BYTES, mbar0 + 8, P.sc1, l_ptr, l_seg, g.nb, lane, g.U > 3);
-    }
+    mk_seg_load<TYPE>(P.buf1, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 1);
+    if (l2_budget > 0) { const int r0 = mk_l2_first_row(g); mk_l2_rows<TYPE>(A, g, r0, r0 + mk_l2_depth<TYPE>(g, l2_budget) + 1); }
+    return (g.U / g.NSEG) * g.nb * BB;
+}
+// L2 prefetch only (the phase after the next one, when the next one leaves budget): rows [0, depth)
+template <int TYPE>
+__device__ __forceinline__ void matvec_prefetch_l2_only(const StreamArgs& A, int l2_budget) {
+    const MkGeo g = mk_geo(A);
+    mk_l2_rows<TYPE>(A, g, 0, mk_l2_depth<TYPE>(g, l2_budget));
 }
 
-// precondition: the pipe holds this warp's segments 0, 1 (registers) and, in deep mode, 2, 3 (TMA stages): matvec_prefetch
+// precondition: the pipe holds this warp's segments 0, 1 (matvec_prefetch).  s_w: staging area of the norm weights at the top
+// of dynamic shared memory; w_staged: they were already requested there (cp.async, before the barrier) by the look-ahead.
 template <int TYPE>
-__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* exp_lut, MkPipe& P, bool deep, const int4* stage0, unsigned stage0_smem, unsigned mbar0,
+__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, const uint16_t* exp_lut, MkPipe& P, int l2_budget,
                              const CommDev& comm, unsigned xseq, unsigned long long* stamp1) {
     const StreamArgs& A = ph.mv;
     const int k = A.k;
@@ -320,10 +330,16 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
     // load cursor: points at segment 2
     int l_i = 0, l_seg = 0;
     MkRowPtr l_ptr = mk_vrow_ptr<TYPE>(M, g, 0, lane);
-    auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); } };
-    advance_load();
-    advance_load();
-    if (deep) { advance_load(); advance_load(); }
+    // every time the load cursor enters a new row, the row l2_depth further down the list is requested into L2
+    const int l2_depth = l2_budget > 0 ? mk_l2_depth<TYPE>(g, l2_budget) : 0;
+    auto advance_load = [&]() {
+        if (++l_seg == NSEG) {
+            l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane);
+            if (l2_depth) mk_l2_rows<TYPE>(A, g, l_i + l2_depth, l_i + l2_depth + 1);
+        }
+    };
+    if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); }       // -> segment 1 (already requested)
+    if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); }       // -> segment 2
     MkSeg& buf0 = P.buf0;
     MkSeg& buf1 = P.buf1;
     if (ph.x) {
@@ -333,12 +349,11 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
         const int n = k;
         const int warp = threadIdx.x >> 5;
         float* s_red = (float*)(smem + (size_t)nbp * 40);                // scratch behind the activation arrays
-        float* s_x = s_red + 64;                                          // f32 copy of x, then of the norm weights
-        float* s_w = s_x + n;
+        float* s_x = s_red + 64;                                          // f32 copy of x
         {   // one L2 round trip: every 16-byte chunk of x (and of the norm weights) requested at once
             const int n4 = n >> 2;
             const unsigned sx = (unsigned)__cvta_generic_to_shared(s_x), sw = (unsigned)__cvta_generic_to_shared(s_w);
-            if (ph.norm_w)
+            if (ph.norm_w && !w_staged)
                 for (int i = threadIdx.x; i < n4; i += MK_THREADS)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sw + i * 16), "l"(ph.norm_w + i * 4) : "memory");
             if (ph.red_n) {
@@ -477,45 +492,15 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, const uint16_t* e
             o[rr] = r;
         }
     };
-    if (!deep) {
-        for (int u = 0; u < U; u += 2) {          // two segments (8 KB of Q8_0) in flight per warp at all times
-            acc += mk_seg_dot<TYPE>(buf0, c_seg, aq_l, ad_l, as_l);
-            finish_segment();
-            mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 2 < U);
-            advance_load();
-            if (u + 1 >= U) break;
-            acc += mk_seg_dot<TYPE>(buf1, c_seg, aq_l, ad_l, as_l);
-            finish_segment();
-            mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 3 < U);
-            advance_load();
-        }
-        flush_pending();
-        return;
-    }
-    // deep: four segments in flight per warp, slots rotate register 0, register 1, TMA stage 0, TMA stage 1
-    for (int u = 0; u < U; u += 4) {
+    for (int u = 0; u < U; u += 2) {          // two segments (8 KB of Q8_0) in flight per warp at all times
         acc += mk_seg_dot<TYPE>(buf0, c_seg, aq_l, ad_l, as_l);
         finish_segment();
-        mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 4 < U);
+        mk_seg_load<TYPE>(buf0, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 2 < U);
         advance_load();
         if (u + 1 >= U) break;
         acc += mk_seg_dot<TYPE>(buf1, c_seg, aq_l, ad_l, as_l);
         finish_segment();
-        mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 5 < U);
-        advance_load();
-        if (u + 2 >= U) break;
-        mbar_wait(mbar0, P.par & 1u);
-        P.par ^= 1u;
-        acc += mk_stage_dot<TYPE>(stage0, P.sc0, c_seg, GR, g.last_half_off, lane, aq_l, ad_l, as_l);
-        finish_segment();
-        mk_stage_issue<TYPE>(stage0_smem, mbar0, P.sc0, l_ptr, l_seg, nb, lane, u + 6 < U);
-        advance_load();
-        if (u + 3 >= U) break;
-        mbar_wait(mbar0 + 8, (P.par >> 1) & 1u);
-        P.par ^= 2u;
-        acc += mk_stage_dot<TYPE>(stage0 + MK_STAGE_BYTES / 16, P.sc1, c_seg, GR, g.last_half_off, lane, aq_l, ad_l, as_l);
-        finish_segment();
-        mk_stage_issue<TYPE>(stage0_smem + MK_STAGE_BYTES, mbar0 + 8, P.sc1, l_ptr, l_seg, nb, lane, u + 7 < U);
+        mk_seg_load<TYPE>(buf1, l_ptr, l_seg, nb, GR, g.last_half_off, lane, u + 3 < U);
         advance_load();
     }
     flush_pending();
@@ -719,76 +704,80 @@ __device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsigned xs
 }
 
 
+// look-ahead arguments of the next two MATVEC phases, fetched one word per thread at phase start
+struct MkNext { StreamArgs mv; int wtype; int norm_n; const float* norm_w; };
+static_assert(sizeof(StreamArgs) % 4 == 0 && sizeof(StreamArgs) / 4 + 4 <= 64, "MkNext fetch layout: 64 threads per look-ahead slot");
+
+// flags: 1 look-ahead weight prefetch | 4 norm weights staged before the barrier | 8 every CTA polls the arrival counter |
+//        bits 8..15: L2 look-ahead budget per warp in KB (0 = off)
+#define MK_F_LOOK 1
+#define MK_F_WSTAGE 4
+#define MK_F_POLLCNT 8
+#define MK_TYPE_CALL(T, CALL_Q8, CALL_Q4) do { if ((T) == CC_Q8_0) { CALL_Q8; } else { CALL_Q4; } } while (0)
+
 __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
-                                                                         unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags, const CommDev comm) {
+                                                                         unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags, int wtop_off,
+                                                                         unsigned* err_host, const CommDev comm) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ float s_red[MK_WARPS];
     __shared__ MkPhase s_phs[2];             // phase descriptors, double-buffered: p+1 is fetched while p runs
-    __shared__ StreamArgs s_next;            // arguments of the next MATVEC phase (for the look-ahead prefetch)
-    __shared__ int s_next_type;
-    __shared__ __align__(8) unsigned long long s_mbar[MK_WARPS * MK_STAGES];   // one mbarrier per (warp, TMA stage)
+    __shared__ MkNext s_next[2];             // arguments of the next two MATVEC phases (look-ahead prefetch)
+    __shared__ int s_abort;
     __shared__ __align__(8) unsigned long long s_abar[AT_NBUF];                // attention chunk buffers (TMA completion)
     unsigned apar = 0u;                      // per-buffer wait parity of the attention chunk pipeline
     const unsigned abar0 = (unsigned)__cvta_generic_to_shared(&s_abar[0]);
-    if (threadIdx.x == 0) { for (int i = 0; i < AT_NBUF; i++) mbar_init(abar0 + 8u * i, 1u); }
+    if (threadIdx.x == 0) { for (int i = 0; i < AT_NBUF; i++) mbar_init(abar0 + 8u * i, 1u); s_abort = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    MkPipe pipe;                             // weight prefetch (registers + TMA stages), live across phases and barriers
-    pipe.par = 0u;
-#if MK_DEEP
-    const bool deep = (flags & 2) != 0;      // TMA stages enabled (host: shared memory budget allows the 128 KB staging area)
-#else
-    constexpr bool deep = false;             // experimental TMA stages compiled out (profiles/r01e: slower -- spills + 128 KB less L1)
-#endif
-    uint8_t* work = smem + (deep ? MK_STAGING : 0);       // per-phase working area (activation arrays, attention tiles)
-    const int4* stage0 = (const int4*)(smem + (threadIdx.x >> 5) * (MK_STAGES * MK_STAGE_BYTES));
-    const unsigned stage0_smem = (unsigned)__cvta_generic_to_shared(stage0);
-    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&s_mbar[(threadIdx.x >> 5) * MK_STAGES]);
-    if (deep) {
-        if ((threadIdx.x & 31) == 0) { mbar_init(mbar0, 1u); mbar_init(mbar0 + 8, 1u); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-    }
+    MkPipe pipe;                             // weight prefetch registers, live across phases and barriers
+    uint8_t* work = smem;                    // per-phase working area (activation arrays, attention tiles)
+    float* s_w = (float*)(smem + wtop_off);  // norm weights of the next fused prologue (top of dynamic shared memory)
+    const int l2_budget = ((flags >> 8) & 255) << 10;
     int prefetched = -1;                     // phase index whose first segments sit in the pipe
+    int wstaged = -1;                        // phase index whose norm weights were requested into s_w
     unsigned gen = 0;                        // barriers completed; starts from the value left by the last launch
     if (threadIdx.x == MK_BAR_THREAD) gen = ld_acquire_u32(&bar[32]);
     unsigned xseq = comm.world > 0 ? *comm.seq : 0u;     // exchanges finished so far on this rank (comm.cu)
-    auto fetch_desc = [&](int p) {
-        const int* src = (const int*)(phases + p);
-        int* dst = (int*)&s_phs[p & 1];
+    {
+        const int* src = (const int*)phases;
+        int* dst = (int*)&s_phs[0];
         for (int i = threadIdx.x; i < (int)(sizeof(MkPhase) / 4); i += MK_THREADS) dst[i] = src[i];
-    };
-    fetch_desc(0);
+    }
     for (int p = 0; p < n_phases; p++) {
         // developer profiling, 4 stamps per phase from CTA 0 / thread 0: start, activation ready (MATVEC), rows done, arrived + prefetch issued
         const bool stamp = prof && blockIdx.x == 0 && threadIdx.x == 0;
         if (stamp) { prof[p * 4] = globaltimer_ns(); prof[p * 4 + 1] = 0; }
         __syncthreads();                     // descriptor p is in shared memory (stored one phase ago)
         const MkPhase& s_ph = s_phs[p & 1];
-        // Descriptor p+1 and the arguments of the next MATVEC phase (look-ahead prefetch) are LOADED now, into one register each,
+        // Descriptor p+1 and the arguments of the next MATVEC phases (look-ahead prefetch) are LOADED now, into one register each,
         // and STORED to shared memory after the phase body: a load followed directly by its st.shared would block the thread for
         // an L2 round trip (in-order issue) before it could issue the phase's own loads.
-        static_assert(sizeof(MkPhase) / 4 <= MK_THREADS && sizeof(StreamArgs) / 4 + 1 <= MK_THREADS, "descriptor does not fit one word per thread");
-        const int nx = s_ph.next_matvec;
-        const bool look = (flags & 1) && nx > p && nx < n_phases && prefetched != nx && p + 1 < n_phases;
+        static_assert(sizeof(MkPhase) / 4 <= MK_THREADS, "descriptor does not fit one word per thread");
+        const int nx = s_ph.next_matvec, nx2 = s_ph.next_matvec2;
+        const bool look = (flags & MK_F_LOOK) && nx > p && nx < n_phases && prefetched != nx && p + 1 < n_phases;
         int desc_w = 0, next_w = 0;
         if (p + 1 < n_phases && threadIdx.x < sizeof(MkPhase) / 4) desc_w = ((const int*)(phases + p + 1))[threadIdx.x];
-        if (look) {
-            if (threadIdx.x < sizeof(StreamArgs) / 4) next_w = ((const int*)&phases[nx].mv)[threadIdx.x];
-            else if (threadIdx.x == sizeof(StreamArgs) / 4) next_w = phases[nx].wtype;
+        if (look && threadIdx.x < 128) {
+            const int slot = threadIdx.x >> 6, t = threadIdx.x & 63;
+            const int q = slot == 0 ? nx : nx2;
+            if (q > p && q < n_phases) {
+                const MkPhase* ph = phases + q;
+                constexpr int NW = (int)(sizeof(StreamArgs) / 4);
+                if (t < NW) next_w = ((const int*)&ph->mv)[t];
+                else if (t == NW) next_w = ph->wtype;
+                else if (t == NW + 1) next_w = ph->x && ph->norm_w ? ph->n : 0;
+                else if (t == NW + 2) next_w = ((const int*)&ph->norm_w)[0];
+                else if (t == NW + 3) next_w = ((const int*)&ph->norm_w)[1];
+            } else if (t == (int)(sizeof(StreamArgs) / 4)) next_w = -1;     // no such phase
         }
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
-            if (s_ph.wtype == CC_Q8_0) {
-                if (prefetched != p) matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe, deep, stage0_smem, mbar0);
-                phase_matvec<CC_Q8_0>(s_ph, work, exp_lut, pipe, deep, stage0, stage0_smem, mbar0, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr);
-            } else {
-                if (prefetched != p) matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe, deep, stage0_smem, mbar0);
-                phase_matvec<CC_Q4_0>(s_ph, work, exp_lut, pipe, deep, stage0, stage0_smem, mbar0, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr);
-            }
+            if (prefetched != p) MK_TYPE_CALL(s_ph.wtype, matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe, l2_budget), matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe, l2_budget));
+            MK_TYPE_CALL(s_ph.wtype,
+                         phase_matvec<CC_Q8_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr),
+                         phase_matvec<CC_Q4_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr));
             break;
         case MK_ATTN:
             if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar); else phase_attn<false>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar);
@@ -799,32 +788,48 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         }
         if (stamp) prof[p * 4 + 2] = globaltimer_ns();
         if (p + 1 < n_phases && threadIdx.x < sizeof(MkPhase) / 4) ((int*)&s_phs[(p + 1) & 1])[threadIdx.x] = desc_w;
-        if (look) {
-            if (threadIdx.x < sizeof(StreamArgs) / 4) ((int*)&s_next)[threadIdx.x] = next_w;
-            else if (threadIdx.x == sizeof(StreamArgs) / 4) s_next_type = next_w;
+        if (look && threadIdx.x < 128) {
+            const int slot = threadIdx.x >> 6, t = threadIdx.x & 63;
+            if (t < (int)(sizeof(StreamArgs) / 4) + 4) ((int*)&s_next[slot])[t] = next_w;
         }
-        // look-ahead: request the first two weight segments of the next MATVEC phase before waiting at the barrier, so HBM
-        // keeps streaming through the barrier and through any small (NORMQ / ATTN / ROWS) phases in between
+        // look-ahead: request the first two weight segments of the next MATVEC phase (and, into L2, the rows behind them and the first
+        // rows of the phase after it) before waiting at the barrier, so HBM keeps streaming through the barrier, the prologue and any
+        // small (NORMQ / ATTN / ROWS) phases in between
         const bool more = p + 1 < n_phases;
         const bool xg = s_ph.xgpu != 0;
-        if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);       // its bar.sync also publishes s_next (written at phase start)
+        if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);       // its bar.sync also publishes s_next (written just above)
         if (look) {
-            if (s_next_type == CC_Q8_0) matvec_prefetch<CC_Q8_0>(s_next, pipe, deep, stage0_smem, mbar0); else matvec_prefetch<CC_Q4_0>(s_next, pipe, deep, stage0_smem, mbar0);
+            int used = 0;
+            MK_TYPE_CALL(s_next[0].wtype, used = matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe, l2_budget), used = matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe, l2_budget));
             prefetched = nx;
+            if (l2_budget - used >= 2048 && s_next[1].wtype >= 0)
+                MK_TYPE_CALL(s_next[1].wtype, matvec_prefetch_l2_only<CC_Q8_0>(s_next[1].mv, l2_budget - used), matvec_prefetch_l2_only<CC_Q4_0>(s_next[1].mv, l2_budget - used));
+            if ((flags & MK_F_WSTAGE) && s_next[0].norm_n > 0) {     // immutable norm weights of the next fused prologue: one L2 trip less after the barrier
+                const unsigned sw = (unsigned)__cvta_generic_to_shared(s_w);
+                const float* nw = s_next[0].norm_w;
+                for (int i = threadIdx.x; i < (s_next[0].norm_n >> 2); i += MK_THREADS)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sw + i * 16), "l"(nw + i * 4) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                wstaged = nx;
+            }
         }
         if (stamp) prof[p * 4 + 3] = globaltimer_ns();
-        if (more) { grid_barrier_wait(bar, gridDim.x, gen, comm, xg ? xseq + 1u : 0u); gen++; if (xg) xseq++; }
+        if (more) {
+            grid_barrier_wait(bar, gridDim.x, gen, comm, xg ? xseq + 1u : 0u, (flags & MK_F_POLLCNT) != 0, &s_abort, err_host);
+            gen++; if (xg) xseq++;
+            if (s_abort) break;              // a barrier timed out (a CTA never became resident, or a peer GPU died): bail out, host reports
+        }
     }
     if (comm.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) *comm.seq = xseq;
     if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases * 4] = globaltimer_ns();
 }
 
-// working shared memory of one phase (the TMA staging area of deep mode comes on top, see cc_launch_mega)
+// working shared memory of one phase (the staging area of the norm weights comes on top, see cc_launch_mega)
 size_t cc_mega_smem_for_phase(const MkPhase& ph) {
     if (ph.type == MK_MATVEC) {
         const size_t k = (size_t)ph.mv.k, nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
-        // quants | scales | block sums | prologue: reduction scratch, f32 x, f32 norm weights
-        return nbp * 40 + 256 + (ph.x ? k * 4 : 0) + (ph.x && ph.norm_w ? k * 4 : 0);
+        // quants | scales | block sums | prologue: reduction scratch, f32 x
+        return nbp * 40 + 256 + (ph.x ? k * 4 : 0);
     }
     if (ph.type == MK_ATTN) return (size_t)(3 * ph.at.hd + ((ph.at.max_len + 8 + 3) & ~3) + AT_NBUF * AT_CH * ph.at.hd) * 4 + 64;
     return 1024;
@@ -834,7 +839,7 @@ size_t cc_mega_smem_for_phase(const MkPhase& ph) {
 extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase) {
     if (!dev || n < 2 || !us_per_phase) return CC_ERR_ARG;
     std::vector<MkPhase> tab((size_t)n);
-    for (auto& p : tab) { memset(&p, 0, sizeof(p)); p.type = 99; p.next_matvec = -1; }
+    for (auto& p : tab) { memset(&p, 0, sizeof(p)); p.type = 99; p.next_matvec = -1; p.next_matvec2 = -1; }
     MkPhase* d_tab = nullptr; unsigned* d_bar = nullptr;
     CC_CUDA(dev, cudaMalloc(&d_tab, tab.size() * sizeof(MkPhase)));
     CC_CUDA(dev, cudaMalloc(&d_bar, 4096));
@@ -845,7 +850,7 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
     for (int rep = 0; rep < 4; rep++) {
         CC_CUDA(dev, cudaMemsetAsync(d_bar, 0, 4096, dev->stream));
         cudaEventRecord(e0, dev->stream);
-        int rc = cc_launch_mega(dev, d_tab, n, nullptr, d_bar, 1024, nullptr, nullptr);
+        int rc = cc_launch_mega(dev, d_tab, n, nullptr, d_bar, 1024, 0, nullptr, nullptr);
         if (rc) return rc;
         cudaEventRecord(e1, dev->stream);
         CC_CUDA(dev, cudaEventSynchronize(e1));
@@ -857,17 +862,20 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
     return CC_OK;
 }
 
-int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem, unsigned long long* prof, const CommDev* comm) {
-    static const int base_flags = (getenv("CRABML_MEGA_NOPREFETCH") ? 0 : 1) | (getenv("CRABML_MEGA_FLAGS") ? atoi(getenv("CRABML_MEGA_FLAGS")) : 0);     // developer A/B switches
+// developer A/B switches: CRABML_MEGA_FLAGS replaces the default flag word (see MK_F_* and the L2 budget byte)
+#define MK_DEFAULT_FLAGS (MK_F_LOOK | MK_F_WSTAGE | (24 << 8))
+int cc_mega_flags() {
+    static const int f = getenv("CRABML_MEGA_FLAGS") ? (int)strtol(getenv("CRABML_MEGA_FLAGS"), nullptr, 0) : MK_DEFAULT_FLAGS;
+    return f;
+}
+
+int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem_work, size_t smem_wstage,
+                   unsigned long long* prof, const CommDev* comm) {
+    const int flags = cc_mega_flags();
     int max_ctas_per_sm = 0;
-    int flags = base_flags;
-    {   // deep prefetch needs the 128 KB TMA staging area in front of the phases' working area
-        cudaFuncAttributes fa;
-        CC_CUDA(dev, cudaFuncGetAttributes(&fa, mega_kernel));
-        const size_t limit = 232448 - fa.sharedSizeBytes;          // 227 KB opt-in maximum per CTA on sm_100
-        if (MK_DEEP && getenv("CRABML_MEGA_DEEP") && (flags & 1) && smem + MK_STAGING <= limit) { flags |= 2; smem += MK_STAGING; }   // experimental, off: profiles/r01e
-        else if (getenv("CRABML_MEGA_PAD") && smem + MK_STAGING <= limit) smem += MK_STAGING;      // developer A/B: shared memory size alone
-    }
+    const size_t wtop = (smem_work + 15) & ~(size_t)15;
+    const size_t smem = wtop + smem_wstage;
+    CC_REQUIRE(dev, smem <= 227 * 1024, "megakernel: a phase needs %zu bytes of shared memory", smem);
     if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, mega_kernel, MK_THREADS, smem));
     CC_REQUIRE(dev, max_ctas_per_sm >= 1, "megakernel does not fit on an SM");
@@ -878,7 +886,8 @@ int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, cons
     if (comm) cd = *comm;
     // The grid barrier needs every CTA resident at once.  On a GPU this process owns, a plain launch of sm_count CTAs (1 per SM)
     // is co-resident by construction.  With another tenant on the same GPU (a second process, MPS) a partially scheduled grid
-    // would spin forever: CRABML_MEGA_COOP=1 adds the cooperative launch attribute (all-or-nothing placement).  It is opt-in
+    // cannot finish a barrier: every spin in the kernel is bounded (MkSpin) and ends in CC_ERR_CUDA "megakernel barrier timeout"
+    // instead of a hang; CRABML_MEGA_COOP=1 adds the cooperative launch attribute (all-or-nothing placement).  That is opt-in
     // because a cooperative kernel node costs ~1.3 ms per graph launch on this driver (274 vs 416 tok/s, same call).
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -888,7 +897,7 @@ int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, cons
     attr[0].val.cooperative = getenv("CRABML_MEGA_COOP") ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const uint16_t* lut = dev->exp_lut;
-    CC_CUDA(dev, cudaLaunchKernelEx(&cfg, mega_kernel, phases_dev, n_phases, dyn_dev, bar_dev, lut, prof, flags, (const CommDev)cd));
+    CC_CUDA(dev, cudaLaunchKernelEx(&cfg, mega_kernel, phases_dev, n_phases, dyn_dev, bar_dev, lut, prof, flags, (int)wtop, dev->err_host, (const CommDev)cd));
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }

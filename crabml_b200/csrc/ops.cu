@@ -1,49 +1,24 @@
 // ops.cu -- the small ops around the matvec, one launch per trait call.
 // Compiled with -fmad=false / IEEE div+sqrt so that every op reproduces the reference's f32
-// arithmetic; only reduction ORDER differs (tree instead of sequential).
+// arithmetic; only reduction ORDER differs (the canonical 512-thread tree of common.cuh instead of sequential).
 #include "common.cuh"
 
-// ---- block reductions ----------------------------------------------------------------------------------
-__device__ __forceinline__ float block_sum(float v, float* sh) {
-    v = warp_sum(v);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if (lane == 0) sh[w] = v;
-    __syncthreads();
-    float t = (int)threadIdx.x < nw ? sh[threadIdx.x] : 0.0f;
-    if (w == 0) t = warp_sum(t);
-    if (threadIdx.x == 0) sh[0] = t;
-    __syncthreads();
-    t = sh[0];
-    __syncthreads();
-    return t;
-}
-__device__ __forceinline__ float block_max(float v, float* sh) {
-    v = warp_max(v);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if (lane == 0) sh[w] = v;
-    __syncthreads();
-    float t = (int)threadIdx.x < nw ? sh[threadIdx.x] : -INFINITY;
-    if (w == 0) t = warp_max(t);
-    if (threadIdx.x == 0) sh[0] = t;
-    __syncthreads();
-    t = sh[0];
-    __syncthreads();
-    return t;
-}
-
 // ---- rms_norm_inplace: primitives/rms_norm.rs:32-47  x /= sqrt(sum(x^2)/n + eps), no weight ------------
-__global__ void rms_norm_kernel(float* x, int64_t cols, float eps) {
-    __shared__ float sh[32];
+// canonical 512-thread order (common.cuh); cols % 4 == 0 is implied by the reference's own assert (cols % 32 == 0)
+__global__ void __launch_bounds__(CC_RED_THREADS) rms_norm_kernel(float* x, int64_t cols, float eps) {
+    __shared__ float sh[CC_RED_WARPS];
     float* v = x + (int64_t)blockIdx.x * cols;
     float s = 0.0f;
-    for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) s += v[i] * v[i];
-    s = block_sum(s, sh);
+    const int64_t n4 = cols >> 2;
+    for (int64_t i = threadIdx.x; i < n4; i += CC_RED_THREADS) { const float* c = v + 4 * i; s += cc_sq4(make_float4(c[0], c[1], c[2], c[3])); }
+    if ((cols & 3) && threadIdx.x == 0) for (int64_t i = n4 * 4; i < cols; i++) s += v[i] * v[i];
+    s = cc_block_sum_512(s, sh);
     float rms = sqrtf(s / (float)cols + eps);
-    for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) v[i] = v[i] / rms;
+    for (int64_t i = threadIdx.x; i < cols; i += CC_RED_THREADS) v[i] = v[i] / rms;
 }
 int cc_launch_rms_norm(cc_device* dev, float* x, int64_t rows, int64_t cols, float eps) {
     if (rows == 0 || cols == 0) return CC_OK;
-    rms_norm_kernel<<<(unsigned)rows, 256, 0, dev->stream>>>(x, cols, eps);
+    rms_norm_kernel<<<(unsigned)rows, CC_RED_THREADS, 0, dev->stream>>>(x, cols, eps);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }
@@ -53,25 +28,24 @@ int cc_launch_rms_norm(cc_device* dev, float* x, int64_t rows, int64_t cols, flo
 // ---- softmax_inplace: primitives/softmax.rs:39-54 with the f16 exp LUT (quirk B4) ---------------------------
 __device__ __forceinline__ float exp_cached(float v, const uint16_t* lut) { return h2f_bits(lut[f2h_bits(v)]); }
 
-__global__ void softmax_kernel(float* x, int64_t cols, const uint16_t* __restrict__ lut) {
-    __shared__ float sh[32];
+__global__ void __launch_bounds__(CC_RED_THREADS) softmax_kernel(float* x, int64_t cols, const uint16_t* __restrict__ lut) {
+    __shared__ float sh[CC_RED_WARPS];
     float* v = x + (int64_t)blockIdx.x * cols;
     float m = -INFINITY;
-    for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, v[i]);
-    m = block_max(m, sh);
+    for (int64_t i = threadIdx.x; i < cols; i += CC_RED_THREADS) m = fmaxf(m, v[i]);
+    m = cc_block_max_512(m, sh);
     float s = 0.0f;
-    for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) {
+    for (int64_t i = threadIdx.x; i < cols; i += CC_RED_THREADS) {
         float e = exp_cached(v[i] - m, lut);
         v[i] = e;
         s += e;
     }
-    s = block_sum(s, sh);
-    for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) v[i] = v[i] / s;
+    s = cc_block_sum_512(s, sh);          // canonical order (common.cuh): same bits as the fused attention kernels
+    for (int64_t i = threadIdx.x; i < cols; i += CC_RED_THREADS) v[i] = v[i] / s;
 }
 int cc_launch_softmax(cc_device* dev, float* x, int64_t rows, int64_t cols) {
     if (rows == 0 || cols == 0) return CC_OK;
-    int threads = cols >= 1024 ? 256 : cols >= 128 ? 128 : 32;
-    softmax_kernel<<<(unsigned)rows, threads, 0, dev->stream>>>(x, cols, dev->exp_lut);
+    softmax_kernel<<<(unsigned)rows, CC_RED_THREADS, 0, dev->stream>>>(x, cols, dev->exp_lut);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }

@@ -169,8 +169,31 @@ def test_lazy_7b_shaped_layer(wt, ct):
             r.close()
         finally:
             dev.close()
+    # Every mode reduces with the same grouping (canonical orders, csrc/common.cuh): the recorded/fused kernels and the megakernel
+    # are BIT-IDENTICAL to the eager per-op kernels, which tests/test_gpu_matvec.py and test_gpu_ops.py pin to the oracle within
+    # 1e-6 * sum|terms| -- so those bounds cover the benchmarked megakernel by transitivity.
+    assert np.isfinite(res[0]).all() and np.abs(res[0]).max() > 1e-3
     for mode in (1, 2):
-        rel = np.abs(res[mode] - res[0]).max() / np.abs(res[0]).max()
-        assert np.isfinite(res[mode]).all() and rel < 3e-2, (mode, rel)
-    # same arithmetic per element; only reduction groupings differ with the CTA shape (128/256 vs 512 threads)
-    assert np.abs(res[1] - res[2]).max() / np.abs(res[0]).max() < 3e-2
+        np.testing.assert_array_equal(res[mode].view(np.uint32), res[0].view(np.uint32), err_msg=f"lazy={mode} vs eager")
+
+
+@pytest.mark.parametrize("fname", ["tinyllamas-stories-15m-q8_0.gguf", "tinyllamas-stories-15m-q4_0.gguf"])
+@pytest.mark.parametrize("f16_kv", [False, True])
+def test_execution_modes_bit_identical_on_fixture(fixture_path, fname, f16_kv):
+    """eager / CUDA-graph / megakernel on the reference's own GGUF fixtures (head_dim 48: unquantised attention output path,
+    rows of 288 and 768: ragged last group), 24 positions so the softmax spans more than one warp."""
+    from crabml_b200 import runner as R
+    path = fixture_path(fname)
+    seq = (PROMPT_IDS + CASES[0][2])[:21] + [5, 6, 7]
+    res = {}
+    for lazy in (0, 1, 2):
+        dev = make_device(lazy=lazy)
+        try:
+            conf, w, _ = R.load_gguf(path, dev)
+            r = R.LlamaRunner(dev, conf, w, 64, f16_kv=f16_kv)
+            res[lazy] = np.stack([r.forward([t], p).copy() for p, t in enumerate(seq)])
+            r.close()
+        finally:
+            dev.close()
+    for mode in (1, 2):
+        np.testing.assert_array_equal(res[mode].view(np.uint32), res[0].view(np.uint32), err_msg=f"lazy={mode} vs eager")

@@ -67,6 +67,53 @@ __global__ void k_warpchunk(const int4* __restrict__ in, size_t n_chunks, int* o
     if (acc == 0x12345678) *out = acc;
 }
 
+
+// C: L2-resident read bandwidth: the same `n` int4 are read `reps` times inside one launch (warp-chunk pattern, double-buffered)
+__global__ void k_l2_reread(const int4* __restrict__ in, size_t n, int reps, int* out) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    int acc = 0;
+    for (int r = 0; r < reps; r++)
+        for (size_t i = tid; i + 7 * stride < n; i += 8 * stride) {
+            int4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = ld_nc(in + i + j * stride);
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc += v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
+        }
+    if (acc == 0x12345678) *out = acc;
+}
+// D: cp.async.bulk.prefetch.L2 of a region (each thread one `chunk`-byte piece), optional wait, then read it: does the bulk L2
+//    prefetch work, and how fast is the read afterwards?  stamps: [0] start, [1] prefetch issued, [2] read done (CTA 0, ns)
+__global__ void k_prefetch_then_read(const int4* __restrict__ in, size_t bytes, unsigned chunk, unsigned wait_ns, int do_pf, int* out, unsigned long long* stamps) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    if (do_pf)
+        for (size_t off = tid * chunk; off < bytes; off += nthreads * chunk) {
+            unsigned sz = (unsigned)(bytes - off < chunk ? bytes - off : chunk);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)in + off), "r"(sz) : "memory");
+        }
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    while (true) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); if (t - t0 >= wait_ns) break; }
+    unsigned long long t2;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t2));
+    size_t n = bytes / 16;
+    int acc = 0;
+    for (size_t i = tid; i + 7 * nthreads < n; i += 8 * nthreads) {
+        int4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = ld_nc(in + i + j * nthreads);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
+    }
+    __syncthreads();
+    unsigned long long t3;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t3));
+    if (threadIdx.x == 0) { unsigned long long* s = stamps + blockIdx.x * 4; s[0] = t0; s[1] = t1; s[2] = t2; s[3] = t3; }
+    if (acc == 0x12345678) *out = acc;
+}
+
 template <class F>
 static float timeit(F f, int reps = 5) {
     cudaEvent_t e0, e1;
@@ -105,6 +152,35 @@ int main(int argc, char** argv) {
         printf("B 48MB CH=8 db=1 ctas/sm=%d: %7.2f us  %7.1f GB/s\n", cps, ms * 1e3, small / ms / 1e6);
         ms = timeit([&] { rot = (rot + 1) % 8; k_gridstride<8, true><<<sms * cps, 256>>>(buf + rot * (small / 16), small / 16, out); }, 8);
         printf("A 48MB U=8 ctas/sm=%d: %7.2f us  %7.1f GB/s\n", cps, ms * 1e3, small / ms / 1e6);
+    }
+
+    // L2-resident re-read (one launch, `reps` passes)
+    for (size_t mb : {16, 32, 64, 96}) {
+        size_t nn = (mb << 20) / 16; int reps = 20;
+        float ms = timeit([&] { k_l2_reread<<<sms * 2, 512>>>(buf, nn, reps, out); }, 3);
+        printf("C L2 reread %3zu MB x %d: %7.1f GB/s\n", mb, reps, (double)(mb << 20) * reps / ms / 1e6);
+    }
+    // bulk L2 prefetch, wait, read: per-CTA max of (read time); fresh region every run (rotating through the big buffer)
+    {
+        unsigned long long* st; cudaMalloc(&st, sms * 4 * 8);
+        unsigned long long h[148 * 4];
+        int rot = 0;
+        for (size_t mb : {16, 48, 96})
+            for (int pf = 0; pf < 2; pf++)
+                for (unsigned chunk : {4096u, 16384u})
+                    for (unsigned wait_us : {0u, 20u, 40u}) {
+                        if (!pf && chunk != 4096u) continue;
+                        size_t bytes_r = mb << 20;
+                        rot = (rot + 1) % 4;
+                        const int4* base = buf + (size_t)rot * ((size_t)100 << 20) / 16;
+                        k_prefetch_then_read<<<sms, 512>>>(base, bytes_r, chunk, wait_us * 1000, pf, out, st);
+                        cudaDeviceSynchronize();
+                        cudaMemcpy(h, st, sizeof(h), cudaMemcpyDeviceToHost);
+                        unsigned long long t0 = ~0ull, tpf = 0, t2 = ~0ull, t3 = 0;
+                        for (int b = 0; b < sms; b++) { if (h[b*4] < t0) t0 = h[b*4]; if (h[b*4+1] > tpf) tpf = h[b*4+1]; if (h[b*4+2] < t2) t2 = h[b*4+2]; if (h[b*4+3] > t3) t3 = h[b*4+3]; }
+                        printf("D %3zu MB pf=%d chunk=%5u wait=%2u us: issue %6.2f us, read %7.2f us = %7.1f GB/s, total %7.2f us\n", mb, pf, chunk, wait_us,
+                               (tpf - t0) / 1e3, (t3 - t2) / 1e3, bytes_r / ((t3 - t2) / 1e9) / 1e9, (t3 - t0) / 1e3);
+                    }
     }
     return 0;
 }
