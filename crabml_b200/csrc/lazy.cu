@@ -92,7 +92,7 @@ LazyState* cc_lazy_create(cc_device* dev) {
     for (int i = 0; i < LZ_DYN_SLOTS; i++)
         if (cudaMallocHost(&lz->dyn_host[i], lz->dyn_cap) != cudaSuccess || cudaEventCreateWithFlags(&lz->dyn_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete lz; return nullptr; }
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
-    if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 4 * 4096);
+    if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 8 * 4097);
     if (cudaMalloc(&lz->bar_dev, 4096) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 4096) != cudaSuccess) { delete lz; return nullptr; }
     if (!dev->err_host) {
         if (cudaHostAlloc((void**)&dev->err_host, 64, cudaHostAllocMapped) != cudaSuccess) { delete lz; return nullptr; }
@@ -584,7 +584,7 @@ int cc_lazy_flush(cc_device* dev) {
             cudaError_t e = rc ? cudaSuccess : cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
             if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
             if (!rc) {
-                if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue : 0)); }
+                if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue + 1024 * (ph.mv.k >> 10) : 0)); }
                 rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem, P.mega_wstage,
                                                P.phases.size() < 4000 ? lz->prof_dev : nullptr, cc_comm_dev(dev)) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);
@@ -643,8 +643,8 @@ extern "C" CC_API int cc_lazy_mega_profile(cc_device* dev, unsigned long long* t
     if (!dev || !dev->lz || !dev->lz->prof_dev || !ts || !types || !n_out) return CC_ERR_ARG;
     cudaStreamSynchronize(dev->stream);
     int n = (int)dev->lz->prof_types.size();
-    if ((n + 1) * 4 > cap) return CC_ERR_ARG;          // 4 stamps per phase: start, activation ready, rows done, arrived
-    if (cudaMemcpy(ts, dev->lz->prof_dev, (size_t)(n + 1) * 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return CC_ERR_CUDA;
+    if ((n + 1) * 8 > cap) return CC_ERR_ARG;          // 8 stamps per phase (mega.cu MK_PROF_SLOTS)
+    if (cudaMemcpy(ts, dev->lz->prof_dev, (size_t)(n + 1) * 8 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return CC_ERR_CUDA;
     for (int i = 0; i < n; i++) types[i] = dev->lz->prof_types[i];
     *n_out = n;
     return CC_OK;

@@ -102,7 +102,7 @@ __device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblock
             if (lane == 31) st_release_u32(&bar[32], gen + 1u);
         } else if (lane == 31) {
             MkSpin sp;
-            if (poll_counter && !xseq) { while (ld_acquire_u32(&bar[0]) != target) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }
+            if (poll_counter && !xseq) { while ((int)(ld_acquire_u32(&bar[0]) - target) < 0) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }   // fast CTAs may already have arrived at the NEXT barrier
             else { while (ld_acquire_u32(&bar[32]) != gen + 1u) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }
         }
         if (!ok) *s_abort = 1;
@@ -219,6 +219,9 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@!p bra MK_WAIT_%=;\n}\n" ::"r"(mbar), "r"(parity) : "memory");
 }
+// look-ahead arguments of a coming MATVEC phase, fetched one word per thread at phase start (64 threads per slot)
+struct MkNext { StreamArgs mv; int wtype; int norm_n; const float* norm_w; };
+static_assert(sizeof(StreamArgs) % 4 == 0 && sizeof(StreamArgs) / 4 + 4 <= 64, "MkNext fetch layout: 64 threads per look-ahead slot");
 struct MkPipe { MkSeg buf0, buf1; };      // register stages of the weight stream, live across phases and barriers
 
 // L2 look-ahead: cp.async.bulk.prefetch.L2 (TMA, fire-and-forget, no registers, no shared memory) pulls whole weight rows into
@@ -227,6 +230,9 @@ struct MkPipe { MkSeg buf0, buf1; };      // register stages of the weight strea
 __device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// the same with ordinary prefetch instructions (CCTL.E.PF2): one 128-byte line per lane, 4 KB per warp instruction, non-blocking
+__device__ __forceinline__ void l2_prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// (the L2 byte budget carries the choice in its bit 0: 1 = line prefetches, 0 = bulk TMA prefetches)
 
 // geometry of one MATVEC phase for this warp
 struct MkGeo {
@@ -268,9 +274,20 @@ __device__ __forceinline__ MkRowPtr mk_vrow_ptr(const StreamMats& M, const MkGeo
 // L2 prefetch of the virtual rows [i0, i1) of this warp's row list (clipped to the list): lane j takes row i0 + j, one bulk
 // request for the row's quants and one for its f16 scales (skipped when the scale row is not a multiple of 16 bytes).
 template <int TYPE>
-__device__ __forceinline__ void mk_l2_rows(const StreamArgs& A, const MkGeo& g, int i0, int i1) {
+__device__ __forceinline__ void mk_l2_rows(const StreamArgs& A, const MkGeo& g, int i0, int i1, bool lines) {
     constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
     const int nv = g.U / g.NSEG;
+    if (lines) {          // the whole warp walks the rows: lane l takes the lines l, l + 32, ... of a row
+        const int lane = threadIdx.x & 31;
+        const int qbytes = g.nb * BB, sbytes = g.nb * 2;
+        if (i1 > nv) i1 = nv;
+        for (int i = i0; i < i1; i++) {
+            const MkRowPtr p = mk_vrow_ptr<TYPE>(A.mats, g, i, 0);
+            for (int off = lane * 128; off < qbytes; off += 4096) l2_prefetch_line(p.q + off);
+            if (lane * 128 < sbytes) l2_prefetch_line((const uint8_t*)p.d + lane * 128);
+        }
+        return;
+    }
     const int i = i0 + (int)(threadIdx.x & 31);
     if (i < i1 && i < nv) {
         const MkRowPtr p = mk_vrow_ptr<TYPE>(A.mats, g, i, 0);
@@ -301,21 +318,21 @@ __device__ __forceinline__ int matvec_prefetch(const StreamArgs& A, MkPipe& P, i
     auto advance_load = [&]() { if (++l_seg == g.NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(A.mats, g, ++l_i, lane); } };
     mk_seg_load<TYPE>(P.buf0, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 0); advance_load();
     mk_seg_load<TYPE>(P.buf1, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 1);
-    if (l2_budget > 0) { const int r0 = mk_l2_first_row(g); mk_l2_rows<TYPE>(A, g, r0, r0 + mk_l2_depth<TYPE>(g, l2_budget) + 1); }
+    if (l2_budget > 0) { const int r0 = mk_l2_first_row(g); mk_l2_rows<TYPE>(A, g, r0, r0 + mk_l2_depth<TYPE>(g, l2_budget) + 1, l2_budget & 1); }
     return (g.U / g.NSEG) * g.nb * BB;
 }
 // L2 prefetch only (the phase after the next one, when the next one leaves budget): rows [0, depth)
 template <int TYPE>
 __device__ __forceinline__ void matvec_prefetch_l2_only(const StreamArgs& A, int l2_budget) {
     const MkGeo g = mk_geo(A);
-    mk_l2_rows<TYPE>(A, g, 0, mk_l2_depth<TYPE>(g, l2_budget));
+    mk_l2_rows<TYPE>(A, g, 0, mk_l2_depth<TYPE>(g, l2_budget), l2_budget & 1);
 }
 
 // precondition: the pipe holds this warp's segments 0, 1 (matvec_prefetch).  s_w: staging area of the norm weights at the top
 // of dynamic shared memory; w_staged: they were already requested there (cp.async, before the barrier) by the look-ahead.
 template <int TYPE>
-__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, const uint16_t* exp_lut, MkPipe& P, int l2_budget,
-                             const CommDev& comm, unsigned xseq, unsigned long long* stamp1) {
+__device__ int phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, const uint16_t* exp_lut, MkPipe& P, int l2_budget,
+                             const CommDev& comm, unsigned xseq, unsigned long long* stamp1, const MkNext* early_next, int next_w) {
     const StreamArgs& A = ph.mv;
     const int k = A.k;
     const MkGeo g = mk_geo(A);
@@ -335,7 +352,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
     auto advance_load = [&]() {
         if (++l_seg == NSEG) {
             l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane);
-            if (l2_depth) mk_l2_rows<TYPE>(A, g, l_i + l2_depth, l_i + l2_depth + 1);
+            if (l2_depth) mk_l2_rows<TYPE>(A, g, l_i + l2_depth, l_i + l2_depth + 1, l2_budget & 1);
         }
     };
     if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); }       // -> segment 1 (already requested)
@@ -375,6 +392,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
             }
             asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             __syncthreads();
+            if (stamp1) stamp1[3] = globaltimer_ns();          // x (and the norm weights) are in shared memory
         }
         float rms = 1.0f;
         if (ph.norm_w) {
@@ -389,6 +407,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
             for (int w = 0; w < MK_WARPS; w++) t += s_red[w];
             rms = sqrtf(t / (float)n + ph.eps);
         }
+        if (stamp1) stamp1[4] = globaltimer_ns();              // rms known
         if (ph.orig && blockIdx.x == 0)                              // Tensor::dup of the un-normalised row (llama2.rs:227,607)
             for (int i = threadIdx.x; i < (n >> 2); i += MK_THREADS) ((float4*)ph.orig)[i] = ((const float4*)s_x)[i];
         // quantise: 4 consecutive elements per thread, 8 threads per 32-block, 64 blocks per pass (same arithmetic per element as
@@ -439,6 +458,10 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
                 if constexpr (TYPE == CC_Q4_0) s_s[i] = i < nb ? __ldcg(gs + i) : 0;
             }
         }
+    }
+    if (early_next && threadIdx.x < 128) {      // look-ahead arguments (loaded at phase start) become visible with the barrier below
+        const int slot = threadIdx.x >> 6, t = threadIdx.x & 63;
+        if (t < (int)(sizeof(StreamArgs) / 4) + 4) ((int*)&early_next[slot])[t] = next_w;
     }
     __syncthreads();
     if (stamp1) *stamp1 = globaltimer_ns();
@@ -504,6 +527,13 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
         advance_load();
     }
     flush_pending();
+    // this warp is done: its register stages are free, so it requests its first segments of the next MATVEC phase right away instead
+    // of idling until the slowest warp of the CTA reaches the barrier (the tail of a phase becomes prefetch time)
+    int used = 0;
+    if (early_next) {
+        if (early_next[0].wtype == CC_Q8_0) used = matvec_prefetch<CC_Q8_0>(early_next[0].mv, P, l2_budget); else used = matvec_prefetch<CC_Q4_0>(early_next[0].mv, P, l2_budget);
+    }
+    return used;          // bytes of this warp's share of the next phase (0 unless the look-ahead was issued here)
 }
 
 // ---- ATTN phase: arithmetic of fused.cu attn_decode_kernel, heads dealt to CTAs.  The K (then V) rows of the head are
@@ -704,15 +734,16 @@ __device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsigned xs
 }
 
 
+#define MK_PROF_SLOTS 8      // developer profiling: u64 stamps per phase (CTA 0 / thread 0): 0 start, 1 activation ready, 2 rows done, 3 arrived, 4 x staged, 5 rms known
 // look-ahead arguments of the next two MATVEC phases, fetched one word per thread at phase start
-struct MkNext { StreamArgs mv; int wtype; int norm_n; const float* norm_w; };
-static_assert(sizeof(StreamArgs) % 4 == 0 && sizeof(StreamArgs) / 4 + 4 <= 64, "MkNext fetch layout: 64 threads per look-ahead slot");
 
-// flags: 1 look-ahead weight prefetch | 4 norm weights staged before the barrier | 8 every CTA polls the arrival counter |
+// flags: 1 look-ahead weight prefetch | 4 norm weights staged before the barrier | 8 every CTA polls the arrival counter | 16 | 32 |
 //        bits 8..15: L2 look-ahead budget per warp in KB (0 = off)
 #define MK_F_LOOK 1
 #define MK_F_WSTAGE 4
 #define MK_F_POLLCNT 8
+#define MK_F_L2LINES 16        // L2 look-ahead with per-lane line prefetches instead of bulk (TMA) prefetches
+#define MK_F_EARLY 32          // a warp requests its first segments of the next MATVEC phase as soon as IT has finished its rows
 #define MK_TYPE_CALL(T, CALL_Q8, CALL_Q4) do { if ((T) == CC_Q8_0) { CALL_Q8; } else { CALL_Q4; } } while (0)
 
 __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
@@ -733,7 +764,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     MkPipe pipe;                             // weight prefetch registers, live across phases and barriers
     uint8_t* work = smem;                    // per-phase working area (activation arrays, attention tiles)
     float* s_w = (float*)(smem + wtop_off);  // norm weights of the next fused prologue (top of dynamic shared memory)
-    const int l2_budget = ((flags >> 8) & 255) << 10;
+    const int l2_budget = (((flags >> 8) & 255) << 10) | ((flags & MK_F_L2LINES) ? 1 : 0);
     int prefetched = -1;                     // phase index whose first segments sit in the pipe
     int wstaged = -1;                        // phase index whose norm weights were requested into s_w
     unsigned gen = 0;                        // barriers completed; starts from the value left by the last launch
@@ -747,7 +778,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     for (int p = 0; p < n_phases; p++) {
         // developer profiling, 4 stamps per phase from CTA 0 / thread 0: start, activation ready (MATVEC), rows done, arrived + prefetch issued
         const bool stamp = prof && blockIdx.x == 0 && threadIdx.x == 0;
-        if (stamp) { prof[p * 4] = globaltimer_ns(); prof[p * 4 + 1] = 0; }
+        if (stamp) { prof[p * MK_PROF_SLOTS] = globaltimer_ns(); prof[p * MK_PROF_SLOTS + 1] = 0; prof[p * MK_PROF_SLOTS + 4] = 0; prof[p * MK_PROF_SLOTS + 5] = 0; }
         __syncthreads();                     // descriptor p is in shared memory (stored one phase ago)
         const MkPhase& s_ph = s_phs[p & 1];
         // Descriptor p+1 and the arguments of the next MATVEC phases (look-ahead prefetch) are LOADED now, into one register each,
@@ -771,13 +802,18 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
                 else if (t == NW + 3) next_w = ((const int*)&ph->norm_w)[1];
             } else if (t == (int)(sizeof(StreamArgs) / 4)) next_w = -1;     // no such phase
         }
+        bool early = false;                  // the MATVEC phase issued the look-ahead itself, warp by warp
+        int early_used = 0;
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
             if (prefetched != p) MK_TYPE_CALL(s_ph.wtype, matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe, l2_budget), matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe, l2_budget));
+            early = look && (flags & MK_F_EARLY);
             MK_TYPE_CALL(s_ph.wtype,
-                         phase_matvec<CC_Q8_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr),
-                         phase_matvec<CC_Q4_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * 4 + 1 : nullptr));
+                         early_used = phase_matvec<CC_Q8_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr,
+                                                            early ? s_next : nullptr, next_w),
+                         early_used = phase_matvec<CC_Q4_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr,
+                                                            early ? s_next : nullptr, next_w));
             break;
         case MK_ATTN:
             if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar); else phase_attn<false>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar);
@@ -786,9 +822,9 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         case MK_REDUCE: phase_reduce(s_ph, comm, xseq, false); break;
         case MK_GATHER: phase_reduce(s_ph, comm, xseq, true); break;
         }
-        if (stamp) prof[p * 4 + 2] = globaltimer_ns();
+        if (stamp) prof[p * MK_PROF_SLOTS + 2] = globaltimer_ns();
         if (p + 1 < n_phases && threadIdx.x < sizeof(MkPhase) / 4) ((int*)&s_phs[(p + 1) & 1])[threadIdx.x] = desc_w;
-        if (look && threadIdx.x < 128) {
+        if (look && !early && threadIdx.x < 128) {
             const int slot = threadIdx.x >> 6, t = threadIdx.x & 63;
             if (t < (int)(sizeof(StreamArgs) / 4) + 4) ((int*)&s_next[slot])[t] = next_w;
         }
@@ -799,8 +835,8 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         const bool xg = s_ph.xgpu != 0;
         if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);       // its bar.sync also publishes s_next (written just above)
         if (look) {
-            int used = 0;
-            MK_TYPE_CALL(s_next[0].wtype, used = matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe, l2_budget), used = matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe, l2_budget));
+            int used = early_used;
+            if (!early) MK_TYPE_CALL(s_next[0].wtype, used = matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe, l2_budget), used = matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe, l2_budget));
             prefetched = nx;
             if (l2_budget - used >= 2048 && s_next[1].wtype >= 0)
                 MK_TYPE_CALL(s_next[1].wtype, matvec_prefetch_l2_only<CC_Q8_0>(s_next[1].mv, l2_budget - used), matvec_prefetch_l2_only<CC_Q4_0>(s_next[1].mv, l2_budget - used));
@@ -813,7 +849,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
                 wstaged = nx;
             }
         }
-        if (stamp) prof[p * 4 + 3] = globaltimer_ns();
+        if (stamp) prof[p * MK_PROF_SLOTS + 3] = globaltimer_ns();
         if (more) {
             grid_barrier_wait(bar, gridDim.x, gen, comm, xg ? xseq + 1u : 0u, (flags & MK_F_POLLCNT) != 0, &s_abort, err_host);
             gen++; if (xg) xseq++;
@@ -821,7 +857,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         }
     }
     if (comm.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) *comm.seq = xseq;
-    if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases * 4] = globaltimer_ns();
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) prof[n_phases * MK_PROF_SLOTS] = globaltimer_ns();
 }
 
 // working shared memory of one phase (the staging area of the norm weights comes on top, see cc_launch_mega)

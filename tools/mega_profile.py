@@ -25,27 +25,38 @@ for i in range(40):
     r.forward([100 + i], pos, export=False); pos += 1
 ms = dev.timer_end()
 print(f"40 tokens back to back: {ms / 40 * 1e3:.1f} us per token by CUDA events (kernel time below + inter-launch gap)")
-CAP = 4 * 4096
+SL = 8                                      # stamps per phase (mega.cu MK_PROF_SLOTS)
+CAP = SL * 4097
 ts = (C.c_uint64 * CAP)(); ty = (C.c_int32 * CAP)(); n = C.c_int32(0)
 dev.check(dev.lib.cc_lazy_mega_profile(dev.handle, ts, ty, CAP, C.byref(n)))
 n = n.value
-raw = np.array(ts[:(n + 1) * 4], dtype=np.float64).reshape(n + 1, 4)
+raw = np.array(ts[:(n + 1) * SL], dtype=np.float64).reshape(n + 1, SL)
 t = raw[:, 0]
 d = np.diff(t) / 1e3
-names = {0: "normq", 16 + 3: "qkv matvec(3)", 16 + 1 + 4: "matvec+residual", 16 + 2 + 8: "gate/up silu*mul", 16 + 1: "matvec(1)", 32: "attn", 48: "rows",
-         16 + 1 + 12: "matvec->exchange", 64: "reduce", 80: "gather"}
+base = {0: "normq", 16 + 3: "qkv", 16 + 1 + 4: "mv+res", 16 + 2 + 8: "gate/up", 16 + 1: "mv", 32: "attn", 48: "rows",
+        16 + 1 + 12: "mv->xchg", 64: "reduce", 80: "gather"}
+
+
+def name(code):
+    k = code >> 10
+    b = base.get(code & 1023, str(code & 1023))
+    return f"{b} k={k}K" if k else b
+
+
 agg = collections.defaultdict(list)
 sub = collections.defaultdict(list)
 for i in range(n):
-    k = names.get(ty[i], str(ty[i]))
+    k = name(ty[i])
     agg[k].append(d[i])
-    s0, s1, s2, s3 = raw[i]
+    s0, s1, s2, s3, s4, s5 = raw[i, :6]
     act = (s1 - s0) / 1e3 if s1 > 0 else 0.0            # activation staging / fused prologue (MATVEC only)
-    sub[k].append((act, (s2 - max(s0, s1)) / 1e3, (s3 - s2) / 1e3, (raw[i + 1, 0] - s3) / 1e3))
-print(f"phases {n}, token total {(t[-1] - t[0]) / 1e3:.1f} us (phase time includes the barrier that ends it)")
-print("  CTA 0 breakdown per phase: activation ready | rows of warp 0 done | arrive + look-ahead issue | barrier wait")
+    xs = (s4 - s0) / 1e3 if s4 > 0 else 0.0             # prologue: x staged in shared memory
+    rm = (s5 - s4) / 1e3 if s5 > 0 and s4 > 0 else 0.0  # prologue: rms known
+    qz = (s1 - s5) / 1e3 if s5 > 0 and s1 > 0 else 0.0  # prologue: quantised
+    sub[k].append((act, (s2 - max(s0, s1)) / 1e3, (s3 - s2) / 1e3, (raw[i + 1, 0] - s3) / 1e3, xs, rm, qz))
+print(f"flags {os.environ.get('CRABML_MEGA_FLAGS', 'default')}: phases {n}, token total {(t[-1] - t[0]) / 1e3:.1f} us (phase time includes the barrier that ends it)")
+print("  CTA 0 per phase: activation ready | rows of warp 0 done | arrive + look-ahead issue | barrier wait || prologue: x staged | rms | quantise")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     m = np.mean(np.array(sub[k]), axis=0)
-    print(f"  {k:20s} n={len(v):3d}  sum {sum(v):8.1f} us  avg {np.mean(v):6.2f}  min {min(v):6.2f}  max {max(v):6.2f}   | {m[0]:5.2f} | {m[1]:5.2f} | {m[2]:5.2f} | {m[3]:5.2f}")
-print("first 10 phases:", [(names.get(ty[i], ty[i]), round(d[i], 2)) for i in range(min(10, n))])
+    print(f"  {k:16s} n={len(v):3d}  sum {sum(v):8.1f} us  avg {np.mean(v):6.2f}  min {min(v):6.2f}  max {max(v):6.2f}   | {m[0]:5.2f} | {m[1]:5.2f} | {m[2]:5.2f} | {m[3]:5.2f} || {m[4]:5.2f} | {m[5]:5.2f} | {m[6]:5.2f}")
 dev.close()

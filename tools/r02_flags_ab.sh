@@ -4,5 +4,5 @@
 FL=${1:-"0x1 0x5 0x9 0x1005 0x1805 0x2005 0x180d"}; WL=${2:-Q8_0}
 for f in $FL; do
   echo "== flags $f ($WL)"
-  CRABML_MEGA_FLAGS=$f timeout 150 python tools/mega_profile.py $WL 2>&1 | grep -E "tokens back|token total|n= " | head -9
+  CRABML_MEGA_FLAGS=$f timeout 150 python tools/mega_profile.py $WL 2>&1 | grep -E "tokens back|token total|n= |rror" | head -12
 done
