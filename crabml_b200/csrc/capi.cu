@@ -316,6 +316,8 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
         if (blocks) cc_pool_free(dev, blocks, cls);
     } else if (!rc && b == 1 && cc_stream_supported(wt, k)) {
         rc = cc_launch_matvec_stream_plain(dev, w->buf, dev->act_scratch, (float*)c->base, m, k);     // decode hot path
+    } else if (!rc && cc_prefill_supported(wt, m, k, b)) {
+        rc = cc_launch_prefill_matmul(dev, w->buf, dev->act_scratch, (float*)c->base, m, k, b);       // prefill: dense, tensor cores
     } else if (!rc) rc = cc_launch_matvec(dev, w->buf, dev->act_scratch, xf, (float*)c->base, m, k, b);
     if (rc) { cc_tensor_release(c); return rc; }
     *out = c;

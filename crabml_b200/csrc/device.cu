@@ -102,6 +102,7 @@ extern "C" CC_API void cc_device_destroy(cc_device* dev) {
     cudaStreamSynchronize(dev->stream);
     cc_lazy_destroy(dev);
     cc_comm_destroy(dev);
+    cc_prefill_release(dev);
     for (auto& kv : dev->free_lists)
         for (uintptr_t p : kv.second) cudaFree((void*)p);
     if (dev->act_scratch) cudaFree(dev->act_scratch);

@@ -195,6 +195,7 @@ struct Fuser {
         switch (op.kind) {
         case L_ROPE: case L_CONCAT: case L_BMM: case L_SOFTMAX: P.cacheable = false; break;   // position / length dependent
         case L_COPY_ROWS: P.cacheable = false; break;   // (normally taken by try_copy_rows) host row list would be baked into a graph
+        case L_MATVEC: if (op.b.ndim > 1 && op.b.shape[0] > 1) P.cacheable = false; break;   // batched (prefill) matmul: its scratch may be (re)allocated, never captured
         default: break;
         }
         for (int64_t r : op.rows) P.S((uint64_t)r);
@@ -242,6 +243,7 @@ struct Fuser {
                 if (at != CC_F32) rc = cc_launch_quantize(d, xf, bb * k, at, d->act_scratch);
                 if (rc) return rc;
                 if (bb == 1 && cc_stream_supported(wt, k)) return cc_launch_matvec_stream_plain(d, a.buf, d->act_scratch, (float*)op.out->base, m, k);
+                if (cc_prefill_supported(wt, m, k, bb)) return cc_launch_prefill_matmul(d, a.buf, d->act_scratch, (float*)op.out->base, m, k, bb);
                 return cc_launch_matvec(d, a.buf, d->act_scratch, xf, (float*)op.out->base, m, k, bb);
             }
             }

@@ -87,7 +87,7 @@ __device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblock
         const unsigned target = (gen + 1u) * nblocks;
         bool ok = true;
         if (blockIdx.x == 0) {
-            if (lane == 31) { MkSpin sp; while (ld_acquire_u32(&bar[0]) != target) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }
+            if (lane == 31) { MkSpin sp; while ((int)(ld_acquire_u32(&bar[0]) - target) < 0) if (sp.expired(bar, err_host, 1u)) { ok = false; break; } }   // (poll mode: the others may already be arriving at the next barrier)
             if (xseq) {                                     // kernel-uniform: the whole warp takes this branch together
                 __syncwarp();                               // every local CTA has arrived: all partial rows are in the peers' slots
                 if (lane < comm.world) {                    // one lane per peer: publish and poll in parallel, not rank after rank
@@ -224,15 +224,9 @@ struct MkNext { StreamArgs mv; int wtype; int norm_n; const float* norm_w; };
 static_assert(sizeof(StreamArgs) % 4 == 0 && sizeof(StreamArgs) / 4 + 4 <= 64, "MkNext fetch layout: 64 threads per look-ahead slot");
 struct MkPipe { MkSeg buf0, buf1; };      // register stages of the weight stream, live across phases and barriers
 
-// L2 look-ahead: cp.async.bulk.prefetch.L2 (TMA, fire-and-forget, no registers, no shared memory) pulls whole weight rows into
-// the 126 MB L2 long before the warp that owns them issues its register loads -- across barriers, prologues and small phases --
-// so HBM keeps streaming while the grid synchronises.  src 16-byte aligned, size a multiple of 16.
-__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// the same with ordinary prefetch instructions (CCTL.E.PF2): one 128-byte line per lane, 4 KB per warp instruction, non-blocking
-__device__ __forceinline__ void l2_prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// (the L2 byte budget carries the choice in its bit 0: 1 = line prefetches, 0 = bulk TMA prefetches)
+// (Tried and removed in round 2, profiles/r02a_*, r02b_*: an L2 look-ahead of each warp's coming rows -- cp.async.bulk.prefetch.L2 as
+// well as per-lane prefetch.global.L2 -- made the token 7-10 % SLOWER: a bulk prefetch request occupies its issuing thread for
+// ~9 us per 4 KB, line prefetches cost issue slots at the phase boundary, and the phase bodies already stream at HBM speed.)
 
 // geometry of one MATVEC phase for this warp
 struct MkGeo {
@@ -271,46 +265,10 @@ __device__ __forceinline__ MkRowPtr mk_vrow_ptr(const StreamMats& M, const MkGeo
     return p;
 }
 
-// L2 prefetch of the virtual rows [i0, i1) of this warp's row list (clipped to the list): lane j takes row i0 + j, one bulk
-// request for the row's quants and one for its f16 scales (skipped when the scale row is not a multiple of 16 bytes).
+// Issue the loads of this warp's first two segments of a MATVEC phase (register stages).  Weights are immutable, so this may run
+// long before the phase itself -- across barriers and small phases -- keeping HBM busy while the grid synchronises.
 template <int TYPE>
-__device__ __forceinline__ void mk_l2_rows(const StreamArgs& A, const MkGeo& g, int i0, int i1, bool lines) {
-    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
-    const int nv = g.U / g.NSEG;
-    if (lines) {          // the whole warp walks the rows: lane l takes the lines l, l + 32, ... of a row
-        const int lane = threadIdx.x & 31;
-        const int qbytes = g.nb * BB, sbytes = g.nb * 2;
-        if (i1 > nv) i1 = nv;
-        for (int i = i0; i < i1; i++) {
-            const MkRowPtr p = mk_vrow_ptr<TYPE>(A.mats, g, i, 0);
-            for (int off = lane * 128; off < qbytes; off += 4096) l2_prefetch_line(p.q + off);
-            if (lane * 128 < sbytes) l2_prefetch_line((const uint8_t*)p.d + lane * 128);
-        }
-        return;
-    }
-    const int i = i0 + (int)(threadIdx.x & 31);
-    if (i < i1 && i < nv) {
-        const MkRowPtr p = mk_vrow_ptr<TYPE>(A.mats, g, i, 0);
-        l2_prefetch(p.q, (unsigned)(g.nb * BB));
-        if (((g.nb * 2) & 15) == 0) l2_prefetch(p.d, (unsigned)(g.nb * 2));
-    }
-}
-// first virtual row the L2 look-ahead has to cover: the register stages hold segments 0 and 1
-__device__ __forceinline__ int mk_l2_first_row(const MkGeo& g) { return 2 / g.NSEG; }
-// rows of L2 look-ahead a byte budget buys for this phase (at least 1)
-template <int TYPE>
-__device__ __forceinline__ int mk_l2_depth(const MkGeo& g, int budget_bytes) {
-    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
-    const int d = budget_bytes / (g.nb * BB);
-    return d < 1 ? 1 : (d > 31 ? 31 : d);
-}
-
-// Issue the loads of this warp's first two segments of a MATVEC phase (register stages) and, with an L2 budget, the bulk L2
-// prefetch of the rows behind them.  Weights are immutable, so this may run long before the phase itself -- across barriers
-// and small phases -- keeping HBM busy while the grid synchronises.  Returns the bytes of this warp's share of the phase.
-template <int TYPE>
-__device__ __forceinline__ int matvec_prefetch(const StreamArgs& A, MkPipe& P, int l2_budget) {
-    constexpr int BB = TYPE == CC_Q8_0 ? 32 : 16;
+__device__ __forceinline__ void matvec_prefetch(const StreamArgs& A, MkPipe& P) {
     const int lane = threadIdx.x & 31;
     const MkGeo g = mk_geo(A);
     int l_i = 0, l_seg = 0;
@@ -318,20 +276,12 @@ __device__ __forceinline__ int matvec_prefetch(const StreamArgs& A, MkPipe& P, i
     auto advance_load = [&]() { if (++l_seg == g.NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(A.mats, g, ++l_i, lane); } };
     mk_seg_load<TYPE>(P.buf0, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 0); advance_load();
     mk_seg_load<TYPE>(P.buf1, l_ptr, l_seg, g.nb, g.GR, g.last_half_off, lane, g.U > 1);
-    if (l2_budget > 0) { const int r0 = mk_l2_first_row(g); mk_l2_rows<TYPE>(A, g, r0, r0 + mk_l2_depth<TYPE>(g, l2_budget) + 1, l2_budget & 1); }
-    return (g.U / g.NSEG) * g.nb * BB;
-}
-// L2 prefetch only (the phase after the next one, when the next one leaves budget): rows [0, depth)
-template <int TYPE>
-__device__ __forceinline__ void matvec_prefetch_l2_only(const StreamArgs& A, int l2_budget) {
-    const MkGeo g = mk_geo(A);
-    mk_l2_rows<TYPE>(A, g, 0, mk_l2_depth<TYPE>(g, l2_budget), l2_budget & 1);
 }
 
 // precondition: the pipe holds this warp's segments 0, 1 (matvec_prefetch).  s_w: staging area of the norm weights at the top
 // of dynamic shared memory; w_staged: they were already requested there (cp.async, before the barrier) by the look-ahead.
 template <int TYPE>
-__device__ int phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, const uint16_t* exp_lut, MkPipe& P, int l2_budget,
+__device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, bool x_staged, const uint16_t* exp_lut, MkPipe& P,
                              const CommDev& comm, unsigned xseq, unsigned long long* stamp1, const MkNext* early_next, int next_w) {
     const StreamArgs& A = ph.mv;
     const int k = A.k;
@@ -347,14 +297,7 @@ __device__ int phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w
     // load cursor: points at segment 2
     int l_i = 0, l_seg = 0;
     MkRowPtr l_ptr = mk_vrow_ptr<TYPE>(M, g, 0, lane);
-    // every time the load cursor enters a new row, the row l2_depth further down the list is requested into L2
-    const int l2_depth = l2_budget > 0 ? mk_l2_depth<TYPE>(g, l2_budget) : 0;
-    auto advance_load = [&]() {
-        if (++l_seg == NSEG) {
-            l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane);
-            if (l2_depth) mk_l2_rows<TYPE>(A, g, l_i + l2_depth, l_i + l2_depth + 1, l2_budget & 1);
-        }
-    };
+    auto advance_load = [&]() { if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); } };
     if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); }       // -> segment 1 (already requested)
     if (++l_seg == NSEG) { l_seg = 0; l_ptr = mk_vrow_ptr<TYPE>(M, g, ++l_i, lane); }       // -> segment 2
     MkSeg& buf0 = P.buf0;
@@ -386,7 +329,7 @@ __device__ int phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w
                     if (ph.red_res) { const float4 r4 = __ldcg((const float4*)ph.red_res + i); acc4.x += r4.x; acc4.y += r4.y; acc4.z += r4.z; acc4.w += r4.w; }
                     ((float4*)s_x)[i] = acc4;
                 }
-            } else {
+            } else if (!x_staged) {
                 for (int i = threadIdx.x; i < n4; i += MK_THREADS)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 16), "l"(ph.x + i * 4) : "memory");
             }
@@ -529,11 +472,7 @@ __device__ int phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool w
     flush_pending();
     // this warp is done: its register stages are free, so it requests its first segments of the next MATVEC phase right away instead
     // of idling until the slowest warp of the CTA reaches the barrier (the tail of a phase becomes prefetch time)
-    int used = 0;
-    if (early_next) {
-        if (early_next[0].wtype == CC_Q8_0) used = matvec_prefetch<CC_Q8_0>(early_next[0].mv, P, l2_budget); else used = matvec_prefetch<CC_Q4_0>(early_next[0].mv, P, l2_budget);
-    }
-    return used;          // bytes of this warp's share of the next phase (0 unless the look-ahead was issued here)
+    if (early_next) { if (early_next[0].wtype == CC_Q8_0) matvec_prefetch<CC_Q8_0>(early_next[0].mv, P); else matvec_prefetch<CC_Q4_0>(early_next[0].mv, P); }
 }
 
 // ---- ATTN phase: arithmetic of fused.cu attn_decode_kernel, heads dealt to CTAs.  The K (then V) rows of the head are
@@ -737,12 +676,13 @@ __device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsigned xs
 #define MK_PROF_SLOTS 8      // developer profiling: u64 stamps per phase (CTA 0 / thread 0): 0 start, 1 activation ready, 2 rows done, 3 arrived, 4 x staged, 5 rms known
 // look-ahead arguments of the next two MATVEC phases, fetched one word per thread at phase start
 
-// flags: 1 look-ahead weight prefetch | 4 norm weights staged before the barrier | 8 every CTA polls the arrival counter | 16 | 32 |
-//        bits 8..15: L2 look-ahead budget per warp in KB (0 = off)
+// flags: 1 look-ahead weight prefetch | 4 norm weights staged before the barrier | 8 every CTA polls the arrival counter |
+//        32 per-warp early look-ahead | 64 x of the next fused prologue requested right after the barrier
 #define MK_F_LOOK 1
 #define MK_F_WSTAGE 4
 #define MK_F_POLLCNT 8
-#define MK_F_L2LINES 16        // L2 look-ahead with per-lane line prefetches instead of bulk (TMA) prefetches
+#define MK_F_TESTSTALL 128     // test hook: the last CTA leaves before barrier 2 -> every other CTA must time out, not hang
+#define MK_F_XEARLY 64         // the f32 row of the next fused prologue is requested (cp.async) right after the barrier opens
 #define MK_F_EARLY 32          // a warp requests its first segments of the next MATVEC phase as soon as IT has finished its rows
 #define MK_TYPE_CALL(T, CALL_Q8, CALL_Q4) do { if ((T) == CC_Q8_0) { CALL_Q8; } else { CALL_Q4; } } while (0)
 
@@ -764,9 +704,9 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
     MkPipe pipe;                             // weight prefetch registers, live across phases and barriers
     uint8_t* work = smem;                    // per-phase working area (activation arrays, attention tiles)
     float* s_w = (float*)(smem + wtop_off);  // norm weights of the next fused prologue (top of dynamic shared memory)
-    const int l2_budget = (((flags >> 8) & 255) << 10) | ((flags & MK_F_L2LINES) ? 1 : 0);
     int prefetched = -1;                     // phase index whose first segments sit in the pipe
     int wstaged = -1;                        // phase index whose norm weights were requested into s_w
+    int xstaged = -1;                        // phase index whose f32 input row was requested into its prologue's staging area
     unsigned gen = 0;                        // barriers completed; starts from the value left by the last launch
     if (threadIdx.x == MK_BAR_THREAD) gen = ld_acquire_u32(&bar[32]);
     unsigned xseq = comm.world > 0 ? *comm.seq : 0u;     // exchanges finished so far on this rank (comm.cu)
@@ -803,17 +743,16 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             } else if (t == (int)(sizeof(StreamArgs) / 4)) next_w = -1;     // no such phase
         }
         bool early = false;                  // the MATVEC phase issued the look-ahead itself, warp by warp
-        int early_used = 0;
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
-            if (prefetched != p) MK_TYPE_CALL(s_ph.wtype, matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe, l2_budget), matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe, l2_budget));
+            if (prefetched != p) MK_TYPE_CALL(s_ph.wtype, matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe), matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe));
             early = look && (flags & MK_F_EARLY);
             MK_TYPE_CALL(s_ph.wtype,
-                         early_used = phase_matvec<CC_Q8_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr,
-                                                            early ? s_next : nullptr, next_w),
-                         early_used = phase_matvec<CC_Q4_0>(s_ph, work, s_w, wstaged == p, exp_lut, pipe, l2_budget, comm, xseq, stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr,
-                                                            early ? s_next : nullptr, next_w));
+                         phase_matvec<CC_Q8_0>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, comm, xseq, stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr,
+                                               early ? s_next : nullptr, next_w),
+                         phase_matvec<CC_Q4_0>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, comm, xseq, stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr,
+                                               early ? s_next : nullptr, next_w));
             break;
         case MK_ATTN:
             if (s_ph.at.kv_f16) phase_attn<true>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar); else phase_attn<false>(s_ph, (float*)work, s_red, dyn, exp_lut, abar0, apar);
@@ -833,13 +772,12 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         // small (NORMQ / ATTN / ROWS) phases in between
         const bool more = p + 1 < n_phases;
         const bool xg = s_ph.xgpu != 0;
+        // test hook (tests/test_gpu_robustness.py): one CTA deserts before the third barrier, as if it had never become resident
+        if ((flags & MK_F_TESTSTALL) && p == 2 && blockIdx.x == gridDim.x - 1) return;
         if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);       // its bar.sync also publishes s_next (written just above)
         if (look) {
-            int used = early_used;
-            if (!early) MK_TYPE_CALL(s_next[0].wtype, used = matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe, l2_budget), used = matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe, l2_budget));
+            if (!early) MK_TYPE_CALL(s_next[0].wtype, matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe), matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe));
             prefetched = nx;
-            if (l2_budget - used >= 2048 && s_next[1].wtype >= 0)
-                MK_TYPE_CALL(s_next[1].wtype, matvec_prefetch_l2_only<CC_Q8_0>(s_next[1].mv, l2_budget - used), matvec_prefetch_l2_only<CC_Q4_0>(s_next[1].mv, l2_budget - used));
             if ((flags & MK_F_WSTAGE) && s_next[0].norm_n > 0) {     // immutable norm weights of the next fused prologue: one L2 trip less after the barrier
                 const unsigned sw = (unsigned)__cvta_generic_to_shared(s_w);
                 const float* nw = s_next[0].norm_w;
@@ -854,6 +792,18 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             grid_barrier_wait(bar, gridDim.x, gen, comm, xg ? xseq + 1u : 0u, (flags & MK_F_POLLCNT) != 0, &s_abort, err_host);
             gen++; if (xg) xseq++;
             if (s_abort) break;              // a barrier timed out (a CTA never became resident, or a peer GPU died): bail out, host reports
+            // the barrier is open: the row the next fused prologue normalises is complete -- request it before anything else (descriptor
+            // bookkeeping, geometry, look-ahead loads) so that its L2 round trip overlaps them
+            const MkPhase& nph = s_phs[(p + 1) & 1];
+            if ((flags & MK_F_XEARLY) && nph.type == MK_MATVEC && nph.x && !nph.red_n) {
+                const int nb = nph.mv.k >> 5, nbp = ((((nb + 31) >> 5) + MK_SEG - 1) / MK_SEG) * MK_SEG * 32;
+                const unsigned sx = (unsigned)__cvta_generic_to_shared(work + (size_t)nbp * 40 + 256);      // = s_x of phase_matvec's prologue
+                const float* xg = nph.x;
+                for (int i = threadIdx.x; i < (nph.mv.k >> 2); i += MK_THREADS)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 16), "l"(xg + i * 4) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                xstaged = p + 1;
+            }
         }
     }
     if (comm.world > 0 && blockIdx.x == 0 && threadIdx.x == 0) *comm.seq = xseq;
@@ -899,7 +849,7 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
 }
 
 // developer A/B switches: CRABML_MEGA_FLAGS replaces the default flag word (see MK_F_* and the L2 budget byte)
-#define MK_DEFAULT_FLAGS (MK_F_LOOK | MK_F_WSTAGE | (24 << 8))
+#define MK_DEFAULT_FLAGS (MK_F_LOOK | MK_F_WSTAGE | MK_F_POLLCNT | MK_F_XEARLY)      // profiles/r02c: 2407 us vs 2586 us (0x5) on the same box
 int cc_mega_flags() {
     static const int f = getenv("CRABML_MEGA_FLAGS") ? (int)strtol(getenv("CRABML_MEGA_FLAGS"), nullptr, 0) : MK_DEFAULT_FLAGS;
     return f;

@@ -1,0 +1,49 @@
+"""The persistent megakernel must fail loudly, never hang: every spin in it is bounded (MkSpin, csrc/mega.cu) and a timed-out
+barrier surfaces as CudaError at the next synchronising call.  VERDICT r1 #6 / ADVICE r1 (mega.cu:888)."""
+import os
+import subprocess
+import sys
+import time
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r"""
+import sys, time
+sys.path.insert(0, %r)
+from crabml_b200 import CudaTensorDevice, CudaError, TensorError
+from crabml_b200 import capi, runner as R
+dev = CudaTensorDevice(0, lazy=2)
+conf = R.LlamaConfig(8, 8, 2, 1024, 2048, 64, 512, 1e-5, 128)
+w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=3)
+r = R.LlamaRunner(dev, conf, w, 16)
+t0 = time.time()
+try:
+    r.forward([1], 0)
+    print("NO-ERROR")
+except (CudaError, TensorError) as e:      # the C++ runner reports every failed trait call as its TensorError, like the reference
+    print("ERROR:", e, "after %%.1f s" %% (time.time() - t0))
+r.close(); dev.close()
+print("CLEAN-EXIT")
+""" % ROOT
+
+
+def test_deserting_cta_is_a_timeout_error_not_a_hang():
+    """test hook MK_F_TESTSTALL (0x80): the last CTA leaves before the third grid barrier, i.e. the grid behaves as if one CTA had
+    never become resident (another tenant on the GPU).  Every other CTA must give up after the spin bound, the kernel must drain,
+    and the host must see CC_ERR_CUDA 'megakernel barrier timeout' -- within seconds."""
+    env = dict(os.environ, CRABML_MEGA_FLAGS=str(0x4D | 0x80))
+    t0 = time.time()
+    p = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=120)
+    out = p.stdout + p.stderr
+    assert "ERROR:" in out and "barrier timeout" in out, out
+    assert "CLEAN-EXIT" in out, out
+    assert time.time() - t0 < 90
+
+
+def test_same_child_without_the_hook_runs():
+    p = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ), capture_output=True, text=True, timeout=120)
+    assert "NO-ERROR" in p.stdout and "CLEAN-EXIT" in p.stdout, p.stdout + p.stderr
