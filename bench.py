@@ -33,6 +33,9 @@ WORKLOADS = {
     "llama2-7b-q4_0-q6k": ("LLAMA2_7B", "Q4_0", "Q6_K"),
     "llama2-7b-q4_k": ("LLAMA2_7B", "Q4_K", "Q6_K"),
     "tinyllamas-15m-q8_0": ("TINYLLAMAS_15M", "Q8_0", "Q8_0"),
+    # BASELINE.json config 5: the dense matmuls of a 4096-token prefill (TMA + tcgen05 path, csrc/prefill_gemm.cu); see run_prefill
+    "mistral-7b-q8_0-prefill": ("MISTRAL_7B", "Q8_0", "Q8_0"),
+    "llama2-7b-q8_0-prefill": ("LLAMA2_7B", "Q8_0", "Q8_0"),
 }
 # dram bytes per megakernel launch from the committed ncu --set full capture (profiles/); None until captured
 TRAFFIC = {("llama2-7b-q8_0", 1): 7059924000 + 11929600}     # profiles/r01f_megakernel_ncu.md
@@ -105,7 +108,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU path restated (oracle/), AVX2 order, all host threads, bounded sample
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 3):
+def cpu_reference_tokens_per_s(workload: str, steps: int = 8, warmup: int = 2, sample_layers: int = 8):
     from crabml_b200 import runner as R          # config table + byte accounting only (no GPU use)
     from oracle import oracle as oc
     from oracle.llama_replay import Llama2Runner, LlamaConfig, LlamaWeights
@@ -135,7 +138,7 @@ def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 3):
         elif dt > best * 1.3:
             break
     dev = OracleDevice(thread_num=threads, flags=oc.ORDER_AVX2)
-    n_sample_layers = min(2, conf.n_layers)
+    n_sample_layers = min(sample_layers, conf.n_layers)
 
     def syn(rows, cols, t, tid):
         return OracleTensor.from_cpu(synth_weight(t, rows, cols, SEED, tid, R.synth_scale(t, cols)), [rows, cols], t, dev)
@@ -152,48 +155,101 @@ def cpu_reference_tokens_per_s(workload: str, budget_tokens: int = 3):
         w["down"].append(syn(dim, hid, wt, b + 7)); w["ra"].append(norm()); w["rf"].append(norm())
     tok_embed = syn(conf.vocab_size, dim, wt, 7 * L + 1)
     out_w = syn(conf.vocab_size, dim, ct, 7 * L + 2)
+    # REAL decode steps (warm-up, then `steps` timed tokens, mean) on two models cut from the same weights: 1 layer and
+    # n_sample_layers layers (+ embedding, final norm, classifier).  A full token = the 1-layer token + (L - 1) x the per-layer
+    # difference -- every layer of these shapes costs the same on the CPU (weights stream from DRAM once per token).
     times = {}
     for nl in sorted({1, n_sample_layers}):
         c = LlamaConfig(conf.n_heads, conf.n_kv_heads, nl, dim, hid, conf.seq_len, conf.vocab_size, conf.rms_norm_eps, conf.rope_dim or None)
         lw = LlamaWeights(tok_embed, w["wq"][:nl], w["wk"][:nl], w["wv"][:nl], w["wo"][:nl], w["gate"][:nl], w["down"][:nl], w["up"][:nl],
                           w["ra"][:nl], w["rf"][:nl], norm(), out_w)
-        r = Llama2Runner(OracleTensor, c, lw, dev, 16)
-        r.forward([1], 0)                        # warm-up token
-        best_t = float("inf")
-        for i in range(budget_tokens):
-            t0 = time.perf_counter()
-            r.forward([2 + i], 1 + i)
-            best_t = min(best_t, time.perf_counter() - t0)
-        times[nl] = best_t
+        r = Llama2Runner(OracleTensor, c, lw, dev, warmup + steps + 8)
+        pos = 0
+        for i in range(warmup):
+            r.forward([1 + i], pos); pos += 1
+        t0 = time.perf_counter()
+        for i in range(steps):
+            r.forward([100 + i], pos); pos += 1
+        times[nl] = (time.perf_counter() - t0) / max(1, steps)
     if n_sample_layers > 1:
         per_layer = (times[n_sample_layers] - times[1]) / (n_sample_layers - 1)
-        if per_layer <= 0:                       # timer noise: split the 2-layer time by streamed bytes instead
+        if per_layer <= 0:                       # timer noise: split the sampled time by streamed bytes instead
             lb = 4 * R.weight_bytes(wt, dim, dim) + 3 * R.weight_bytes(wt, hid, dim)
             per_layer = times[n_sample_layers] * lb / (n_sample_layers * lb + R.weight_bytes(ct, conf.vocab_size, dim))
         rest = times[1] - per_layer
     else:
         per_layer, rest = times[1], 0.0
     per_token = per_layer * conf.n_layers + max(rest, 0.0)
-    sample = (f"{n_sample_layers} of {conf.n_layers} layers + classifier of {workload} (same synthetic weights, seed {SEED:#x}), "
-              f"best of {budget_tokens} tokens after 1 warm-up, per-layer time x {conf.n_layers} + classifier; AVX2-order restatement, "
-              f"{threads} threads (fastest count of an ascending probe; {cpus} usable CPUs = affinity capped by the cgroup quota, {oc.hw_threads()} hardware threads)")
-    return 1.0 / per_token, threads, sample, per_token
+    detail = {"layers_timed": n_sample_layers, "layers_model": conf.n_layers, "steps_timed": steps, "warmup_run": warmup,
+              "ms_per_token_1_layer_model": times[1] * 1e3, f"ms_per_token_{n_sample_layers}_layer_model": times[n_sample_layers] * 1e3,
+              "ms_per_layer": per_layer * 1e3, "extrapolated": n_sample_layers < conf.n_layers, "threads": threads, "usable_cpus": cpus,
+              "hw_threads": oc.hw_threads(), "thread_probe": "ascending counts on a 2048-row matvec of the body type, fastest kept"}
+    sample = (f"{steps} timed decode steps (after {warmup} warm-up) of a 1-layer and a {n_sample_layers}-layer cut of {workload} (same synthetic weights, seed "
+              f"{SEED:#x}, embedding + final norm + classifier included); token time = 1-layer token + {conf.n_layers - 1} x per-layer difference; "
+              f"AVX2-order C restatement of the reference, {threads} threads ({cpus} usable CPUs, {oc.hw_threads()} hardware threads)")
+    return 1.0 / per_token, threads, sample, per_token, detail
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    tps, threads, sample, per_token = cpu_reference_tokens_per_s(args.workload)
+    tps, threads, sample, per_token, detail = cpu_reference_tokens_per_s(args.workload, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_token * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
         "config": {"workload": f"{args.workload}-decode-synthetic", "note": "reference CPU path restated in C (oracle/): the Rust reference cannot be built here"},
-        "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample, **detail},
         "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def quick_decode(workload: str, local_rank: int, K: int, W: int, start_pos: int):
+    """Second measurement of the default run: the same decode loop (device-resident and e2e) for another weight type, so that one
+    bench line covers the whole metric (Q8_0 AND Q4_0).  Returns a dict that is embedded in the main JSON line."""
+    from crabml_b200 import CudaTensorDevice
+    from crabml_b200 import runner as R
+    cname, wt_name, ct_name = WORKLOADS[workload]
+    conf = getattr(R, cname)
+    wt, ct = TYPE_ID[wt_name], TYPE_ID[ct_name]
+    dev = CudaTensorDevice(local_rank, lazy=2)
+    try:
+        weights = R.synthetic_weights(dev, conf, wt, ct, seed=SEED)
+        runner = R.LlamaRunner(dev, conf, weights, min(conf.seq_len, start_pos + 2 * (W + K) + 8))
+        bytes_per_token = runner.weight_bytes_per_token()
+        pos, tok = 0, 1
+        for _ in range(start_pos):
+            runner.forward([tok], pos, export=False); pos += 1; tok = (tok * 7 + 3) % conf.vocab_size
+
+        def step_e2e(t, p):
+            lg = runner.forward([t], p, export=True)
+            return int(np.flatnonzero(lg == lg.max())[-1])
+        for _ in range(W):
+            tok = step_e2e(tok, pos); pos += 1
+        dev.synchronize()
+        dev.timer_begin(); t0 = time.perf_counter()
+        for _ in range(K):
+            tok = step_e2e(tok, pos); pos += 1
+        e2e_ms = max(dev.timer_end(), (time.perf_counter() - t0) * 1e3)
+        l0 = dev.launch_count()
+        dev.timer_begin()
+        for i in range(K):
+            runner.forward([(tok * 31 + 7 * i) % conf.vocab_size], pos, export=False); pos += 1
+        val_ms = dev.timer_end()
+        launches = dev.launch_count() - l0
+        peaks, _ = measured_peaks()
+        gbs = bytes_per_token / (val_ms / K * 1e-3) / 1e9
+        out = {"workload": f"{workload}-decode-synthetic", "weights": wt_name, "classifier": ct_name, "value": K / (val_ms * 1e-3), "unit": "tok/s",
+               "ms_per_step": val_ms / K, "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": conf.vocab_size * 4},
+               "gpu_launches_device_resident": int(launches), "steps": K, "warmup": W,
+               "roofline": {"bound": "hbm", "kernel": "mega_kernel" if launches == K else "fused kernels (CUDA graph)", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_per_token, "frac_of_8TBs_nominal": gbs / 8000.0}}
+        runner.close()
+        return out
+    finally:
+        dev.close()
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -241,7 +297,7 @@ def run_b200(args, rank, world, local_rank):
     args.lazy = lazy
     weights = R.synthetic_weights(dev, conf, wt, ct, seed=SEED, plan=plan)
     K, W = args.steps, args.warmup
-    kv_len = min(conf.seq_len, args.start_pos + 2 * (W + K) + 8)
+    kv_len = min(conf.seq_len, args.start_pos + 3 * (W + K) + 8)
     runner = R.LlamaRunner(dev, conf, weights, kv_len, plan=plan)
     bytes_per_token = runner.weight_bytes_per_token()
 
@@ -256,17 +312,29 @@ def run_b200(args, rank, world, local_rank):
 
     for _ in range(W):
         tok = step_e2e(tok, pos); pos += 1
-    # ---- timed region 1: e2e through the runner API with host buffers ---------------------------------------
+    # ---- timed region 1: e2e through the runner's public decode call with HOST buffers ---------------------------------------
+    # ccr_runner_generate_greedy_ex: the prompt id goes host->device, the logits of EVERY step come device->host (pinned staging, async)
+    # and the ids too; the host samples (argmax, sampler.rs:109-116) from those logits inside the timed region and must agree with the
+    # device-side sampler that fed the next step.  No step waits for the host, so the GPU never idles between tokens.
     sampler = ClockSampler(local_rank); sampler.start()
     dev.synchronize(); barrier()
     launches0 = dev.launch_count()
     dev.timer_begin(); t0 = time.perf_counter()
-    for _ in range(K):
-        tok = step_e2e(tok, pos); pos += 1
+    ids, lgs = runner.generate_greedy_logits([tok], K)
+    host_ids = [int(np.flatnonzero(lg == lg.max())[-1]) for lg in lgs]
     e2e_ms_dev = dev.timer_end(); e2e_wall = time.perf_counter() - t0
+    assert host_ids == ids and len(ids) == K, "host sampler and device sampler disagree"
+    pos += K; tok = ids[-1]
     launches_e2e = dev.launch_count() - launches0
     barrier()
     e2e_ms = max_over_ranks(max(e2e_ms_dev, e2e_wall * 1e3))      # host work (sampling) is part of e2e
+    # the synchronous variant (one forward + blocking export + host argmax per token), for comparison
+    dev.synchronize(); barrier()
+    dev.timer_begin(); t0 = time.perf_counter()
+    for _ in range(K):
+        tok = step_e2e(tok, pos); pos += 1
+    e2e_sync_ms = max_over_ranks(max(dev.timer_end(), (time.perf_counter() - t0) * 1e3))
+    barrier()
     # ---- timed region 2: device-resident (no per-step host<->device traffic) -----------------------------------
     toks = [(tok * 31 + 7 * i) % conf.vocab_size for i in range(K)]
     dev.synchronize(); barrier()
@@ -335,8 +403,10 @@ def run_b200(args, rank, world, local_rank):
                        "l2_policy": f"weights streamed once per token ({bytes_per_token / 1e9:.2f} GB >> 126 MB L2): inputs larger than L2",
                        "weight_bytes_per_token": bytes_per_token,
                        "hbm_frac_whole_step": bytes_per_token / (val_ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-            "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": conf.vocab_size * 4,
-                    "ms_per_step": e2e_ms / K},
+            "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": conf.vocab_size * 4 + 8,
+                    "ms_per_step": e2e_ms / K,
+                    "api": "ccr_runner_generate_greedy_ex: sampling on the device feeds the next step, logits + ids exported asynchronously every step, host argmax checked in the timed region",
+                    "synchronous_variant": {"value": streams * K / (e2e_sync_ms * 1e-3), "unit": "tok/s", "api": "ccr_runner_forward + blocking export + host argmax per token"}},
             "gpu_launches": int(launches_e2e),
             "gpu_launches_device_resident": int(launches_val),
             "roofline": roofline,
@@ -349,13 +419,101 @@ def run_b200(args, rank, world, local_rank):
                                  **({k: (st1[k] - st0[k]) / 1e3 / K for k in ("host_us_record", "host_us_fuse", "host_us_submit")} if args.lazy else {})},
         }
         if world == 1 and not args.no_cpu_baseline:
-            tps, threads, sample, _ = cpu_reference_tokens_per_s(args.workload)
-            line["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+            tps, threads, sample, _, detail = cpu_reference_tokens_per_s(args.workload, steps=min(K, 8), warmup=2)
+            line["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample, **detail}
     runner.close()
     dev.close()
+    if rank == 0:
+        if world == 1 and args.workload == "llama2-7b-q8_0" and not args.no_also:
+            # the metric names Q8_0 AND Q4_0: same loop, same shapes, Q4_0 blocks (llama.cpp-style Q4_0 files keep a Q6_K classifier:
+            # run `--workload llama2-7b-q4_0-q6k` for that variant)
+            weights = None
+            try:
+                line["also"] = {"llama2-7b-q4_0": quick_decode("llama2-7b-q4_0", local_rank, K, W, args.start_pos)}
+            except Exception as e:      # the second block must never cost the main line
+                line["also"] = {"llama2-7b-q4_0": {"error": repr(e)}}
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+
+def run_prefill(args, rank, world, local_rank):
+    """BASELINE.json config 5: every matmul_vec of a `--prefill-tokens`-token prompt pass (Tensor::matmul_vec with a (b, k) rhs) on the
+    tensor-core path: per layer wq, wk, wv, wo, ffn_gate, ffn_up, ffn_down on (b, k) activations, then the classifier on the last row.
+    A step = all 225 matmuls once.  This is the DENSE part of a prefill (58 of ~63 TFLOP for Mistral-7B at 4096 tokens); attention,
+    norms and RoPE of a batched forward are not part of this workload (the reference has no batched forward: llama2.rs:111-139 walks
+    the prompt token by token)."""
+    from crabml_b200 import CudaTensor, CudaTensorDevice
+    from crabml_b200 import runner as R
+    if rank != 0:
+        return
+    cname, wt_name, ct_name = WORKLOADS[args.workload]
+    conf = getattr(R, cname)
+    wt, ct = TYPE_ID[wt_name], TYPE_ID[ct_name]
+    b = args.prefill_tokens
+    dev = CudaTensorDevice(local_rank, lazy=0)
+    weights = R.synthetic_weights(dev, conf, wt, ct, seed=SEED)
+    dim, hid = conf.embedding_dim, conf.hidden_dim
+    rng = np.random.default_rng(SEED)
+    x_dim = CudaTensor.new(rng.standard_normal(b * dim).astype(np.float32), [b, dim], dev)
+    x_hid = CudaTensor.new(rng.standard_normal(b * hid).astype(np.float32), [b, hid], dev)
+    x_last = CudaTensor.new(rng.standard_normal(dim).astype(np.float32), [dim], dev)
+    flops = 0
+    for key, kk in (("wq", dim), ("wk", dim), ("wv", dim), ("wo", dim), ("ffn_gate", dim), ("ffn_up", dim), ("ffn_down", hid)):
+        for t in weights[key]:
+            flops += 2 * b * t.shape()[0] * kk
+    wbytes = sum(R.weight_bytes(t.dtype(), *t.shape()) for key in ("wq", "wk", "wv", "wo", "ffn_gate", "ffn_up", "ffn_down") for t in weights[key])
+
+    def step():
+        for l in range(conf.n_layers):
+            for key in ("wq", "wk", "wv", "wo", "ffn_gate", "ffn_up"):
+                weights[key][l].matmul_vec(x_dim)
+            weights["ffn_down"][l].matmul_vec(x_hid)
+        return weights["output_weight"].matmul_vec(x_last)
+    K, W = args.steps, args.warmup
+    for _ in range(W):
+        step()
+    sampler = ClockSampler(local_rank); sampler.start()
+    dev.synchronize()
+    l0 = dev.launch_count()
+    dev.timer_begin()
+    for _ in range(K):
+        step()
+    ms = dev.timer_end()
+    launches = dev.launch_count() - l0
+    # e2e: the activations come from pinned host memory every step and the last-row logits go back
+    host_x = rng.standard_normal(b * dim).astype(np.float32)
+    dev.synchronize()
+    dev.timer_begin(); t0 = time.perf_counter()
+    for _ in range(K):
+        xd = CudaTensor.new(host_x, [b, dim], dev)
+        for l in range(conf.n_layers):
+            for key in ("wq", "wk", "wv", "wo", "ffn_gate", "ffn_up"):
+                weights[key][l].matmul_vec(xd)
+            weights["ffn_down"][l].matmul_vec(x_hid)
+        weights["output_weight"].matmul_vec(x_last).export()
+    e2e_ms = max(dev.timer_end(), (time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop()
+    peaks, peak_src = measured_peaks()
+    tf = flops / (ms / K * 1e-3) / 1e12
+    peak_tf = peaks.get("bf16_tflops_sustained", 1431.9)
+    line = {"metric": "prefill_tokens_per_s", "value": b * K / (ms * 1e-3), "unit": "tok/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operand tiles (dequantised Q8_0 weights, quantised activations), f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}-dense-matmuls-synthetic", "prompt_tokens": b, "weights": wt_name,
+                       "scope": "the 225 matmul_vec calls of a prompt pass (per-call activation quantisation and weight dequantisation included); attention / norms / RoPE of a "
+                                "batched forward are not part of this workload",
+                       "l2_policy": f"{wbytes / 1e9:.2f} GB of weights and {b * hid * 4 / 1e6:.0f} MB activations per step: inputs larger than L2",
+                       "flop_per_step": flops},
+            "e2e": {"value": b * K / (e2e_ms * 1e-3), "unit": "tok/s", "h2d_bytes_per_step": b * dim * 4, "d2h_bytes_per_step": conf.vocab_size * 4, "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "umma_gemm_kernel (prefill_gemm.cu): TMA -> smem ring -> tcgen05.mma kind::f16 -> TMEM -> tcgen05.ld epilogue",
+                         "achieved": tf, "peak": peak_tf, "peak_source": peak_src + " bf16_tflops_sustained", "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                         "note": "whole step (dequantise + quantise + GEMM launches) over the dense FLOPs; the GEMM kernel alone is profiled in profiles/"},
+            "clocks": clocks}
+    print(json.dumps(line))
+    dev.close()
 
 
 def main():
@@ -368,6 +526,8 @@ def main():
     ap.add_argument("--start-pos", type=int, default=32, help="KV-cache length before the timed decode steps")
     ap.add_argument("--lazy", type=int, default=2, help="2 = record+fuse, one persistent megakernel per token (default); 1 = fused kernels in a CUDA graph; 0 = one launch per trait call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefill-tokens", type=int, default=4096)
+    ap.add_argument("--no-also", action="store_true", help="skip the second (Q4_0) measurement of the default run")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"], help="N > 1: shard one token stream (strong scaling, default) or run N independent replicas")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="exchange transport of the sharded path: one-shot NVLink peer stores (default) or the NCCL baseline")
     args = ap.parse_args()
@@ -376,6 +536,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload.endswith("-prefill"):
+        run_prefill(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 

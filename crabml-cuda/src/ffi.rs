@@ -124,6 +124,15 @@ extern "C" {
     pub fn cc_debug_tensor_tap(dev: *mut cc_device, name: *const c_char, x: *const cc_view) -> c_int;
     pub fn cc_dump_debug_tensor(dev: *mut cc_device, name: *const c_char, dst: *mut f32, n: *mut usize) -> c_int;
 
+    // ---- greedy decoding without a host round trip per token (extension) ----
+    pub fn cc_argmax_to_slot(dev: *mut cc_device, x: *const cc_view, slot: i32, hist_index: i64) -> c_int;
+    pub fn cc_copy_rows_from_slot(dev: *mut cc_device, dst: *const cc_view, src: *const cc_view, slot: i32) -> c_int;
+    pub fn cc_slot_set(dev: *mut cc_device, slot: i32, value: i64) -> c_int;
+    pub fn cc_read_history(dev: *mut cc_device, first: i64, count: i64, out: *mut i64) -> c_int;
+    pub fn cc_tensor_export_f32_async(dev: *mut cc_device, src: *const cc_view, dst: *mut f32, n: usize) -> c_int;
+    pub fn cc_host_alloc(dev: *mut cc_device, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn cc_host_free(dev: *mut cc_device, p: *mut c_void);
+
     // ---- test / bench hooks ----
     pub fn cc_test_quantize_activation(
         dev: *mut cc_device,

@@ -134,6 +134,14 @@ def load_library(build_if_missing: bool = True):
         "ccr_runner_forward": (i32, [vp, C.POINTER(i64), i32, i64, vp]),
         "ccr_runner_kv_cache_len": (i64, [vp]),
         "ccr_runner_generate_greedy": (i32, [vp, C.POINTER(i64), i32, i32, i64, C.POINTER(i64), C.POINTER(i32)]),
+        "ccr_runner_generate_greedy_ex": (i32, [vp, C.POINTER(i64), i32, i32, i64, C.POINTER(i64), C.POINTER(i32), vp]),
+        "cc_argmax_to_slot": (i32, [vp, pv, i32, i64]),
+        "cc_copy_rows_from_slot": (i32, [vp, pv, pv, i32]),
+        "cc_slot_set": (i32, [vp, i32, i64]),
+        "cc_read_history": (i32, [vp, i64, i64, C.POINTER(i64)]),
+        "cc_tensor_export_f32_async": (i32, [vp, pv, vp, C.c_size_t]),
+        "cc_host_alloc": (i32, [vp, C.c_size_t, pp]),
+        "cc_host_free": (None, [vp, vp]),
     })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

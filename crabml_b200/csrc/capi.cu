@@ -50,7 +50,7 @@ static bool view_in_bounds(const cc_view* v) {
                    "%s: view [%lld, %lld] does not match the quantized matrix [%lld, %lld]", what, (long long)(v)->shape[0],   \
                    (long long)((v)->ndim == 2 ? (v)->shape[1] : 0), (long long)(v)->buf->rows, (long long)(v)->buf->cols)
 // lazy mode (lazy.cu): after the same argument checks as eager mode the op is queued instead of launched
-enum { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU, L_ALLREDUCE, L_ALLGATHER };
+enum { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU, L_ALLREDUCE, L_ALLGATHER, L_ARGMAX };
 int cc_lazy_record(cc_device* dev, int kind, const cc_view* a, const cc_view* b, cc_buf* out, float f, int64_t i0, int64_t i1, int64_t i2,
                    const int64_t* rows, int n_rows);
 #define LAZY(dev) ((dev)->lz != nullptr && !(dev)->exact)
@@ -274,6 +274,88 @@ extern "C" CC_API int cc_all_gather(cc_device* dev, const cc_view* dst, const cc
     CC_REQUIRE(dev, n % 4 == 0 && n <= CC_COMM_MAX_ELEMS, "all_gather: %lld elements per rank unsupported", (long long)n);
     if (LAZY(dev)) return cc_lazy_record(dev, L_ALLGATHER, dst, src, nullptr, 0, n, 0, 0, nullptr, 0);
     return cc_launch_all_gather(dev, (const float*)src->buf->plane[0], n, (float*)dst->buf->plane[0]);
+}
+
+// ---- greedy decoding without a host round trip per token (extension: not part of the reference's trait) ---------------------------------
+// The sampled token id stays on the device: cc_argmax_to_slot writes it to a slot, the next token's embedding lookup reads it from
+// there (cc_copy_rows_from_slot), so the host can submit token t+1 before token t has finished.  sampler.rs:109-116 semantics (the
+// LAST maximum).  hist_index >= 0 additionally records the id in the device-side history that cc_read_history copies back.
+extern "C" CC_API int cc_argmax_to_slot(cc_device* dev, const cc_view* x, int32_t slot, int64_t hist_index) {
+    CHECK_VIEW(dev, x, "argmax_to_slot");
+    REQUIRE_F32(dev, x, "argmax_to_slot");
+    CC_REQUIRE(dev, view_contiguous(x) && view_len(x) > 0, "argmax_to_slot: tensor must be contiguous and non-empty");
+    CC_REQUIRE(dev, slot >= 0 && slot < CC_N_SLOTS && hist_index < CC_HISTORY_CAP, "argmax_to_slot: slot %d / history index %lld out of range", slot, (long long)hist_index);
+    int rc = cc_ensure_slots(dev);
+    if (rc) return rc;
+    if (LAZY(dev)) return cc_lazy_record(dev, L_ARGMAX, x, nullptr, nullptr, 0, slot, hist_index, 0, nullptr, 0);
+    return cc_launch_argmax(dev, (const float*)x->buf->plane[0], view_len(x), dev->slots + slot, dev->history, nullptr, hist_index);
+}
+// copy_rows_from with ONE row whose index is the content of a device slot
+extern "C" CC_API int cc_copy_rows_from_slot(cc_device* dev, const cc_view* dst, const cc_view* src, int32_t slot) {
+    CHECK_VIEW(dev, dst, "copy_rows_from_slot");
+    CHECK_VIEW(dev, src, "copy_rows_from_slot src");
+    CC_REQUIRE(dev, dst->buf->pooled, "not owned");
+    CC_REQUIRE(dev, view_contiguous(dst) && view_contiguous(src), "copy_rows_from_slot: tensors must be contiguous");
+    CC_REQUIRE(dev, src->ndim == 2, "copy_rows_from_slot: src tensor is not 2d");
+    CC_REQUIRE(dev, slot >= 0 && slot < CC_N_SLOTS, "copy_rows_from_slot: slot %d out of range", slot);
+    int dt = dst->buf->dtype;
+    CC_REQUIRE(dev, dt == CC_F32 || dt == CC_F16, "only f32/f16 can be copied to");
+    int64_t cols = dst->shape[dst->ndim - 1];
+    CC_REQUIRE(dev, cols == src->shape[1] && cols <= view_len(dst), "copy_rows_from_slot: row length mismatch");
+    CC_REQUIRE(dev, !cc_is_quant(src->buf->dtype) || cols == src->buf->cols, "copy_rows_from_slot: row length does not match the quantized matrix");
+    int rc = cc_ensure_slots(dev);
+    if (rc) return rc;
+    if (LAZY(dev)) return cc_lazy_record(dev, L_COPY_ROWS, dst, src, nullptr, 0, 0, 0, slot + 1, nullptr, 0);
+    // NOTE: the id in the slot was produced by argmax over this model's logits, i.e. it is < vocab rows by construction
+    return cc_launch_dequant_rows(dev, src->buf, dev->slots + slot, 1, cols, dst->buf->plane[0], dt);
+}
+extern "C" CC_API int cc_slot_set(cc_device* dev, int32_t slot, int64_t value) {
+    if (!dev) return CC_ERR_ARG;
+    CC_ENTER(dev);
+    CC_REQUIRE(dev, slot >= 0 && slot < CC_N_SLOTS, "slot_set: slot %d out of range", slot);
+    int rc = cc_ensure_slots(dev);
+    if (rc) return rc;
+    FLUSH(dev);
+    CC_CUDA(dev, cudaMemcpyAsync(dev->slots + slot, &value, 8, cudaMemcpyHostToDevice, dev->stream));
+    CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
+    return CC_OK;
+}
+// synchronises, then copies history[first .. first + count) to the host
+extern "C" CC_API int cc_read_history(cc_device* dev, int64_t first, int64_t count, int64_t* out) {
+    if (!dev || !out) return CC_ERR_ARG;
+    CC_ENTER(dev);
+    CC_REQUIRE(dev, first >= 0 && count >= 0 && first + count <= CC_HISTORY_CAP, "read_history: range out of bounds");
+    int rc = cc_ensure_slots(dev);
+    if (rc) return rc;
+    FLUSH(dev);
+    if (count) CC_CUDA(dev, cudaMemcpyAsync(out, dev->history + first, (size_t)count * 8, cudaMemcpyDeviceToHost, dev->stream));
+    CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
+    return cc_check_async_error(dev);
+}
+// export without waiting: the copy is enqueued behind the work queued so far; `dst` must stay valid (and should be pinned: cc_host_alloc)
+// until the next synchronising call
+extern "C" CC_API int cc_tensor_export_f32_async(cc_device* dev, const cc_view* src, float* dst, size_t n) {
+    CHECK_VIEW(dev, src, "export_async");
+    if (!dst) return cc_fail(dev, CC_ERR_ARG, "export_async: dst is NULL");
+    REQUIRE_F32(dev, src, "export_async");
+    CC_REQUIRE(dev, view_contiguous(src), "export_async: tensor is not contiguous");
+    FLUSH(dev);
+    int64_t len = view_len(src);
+    size_t cnt = n < (size_t)len ? n : (size_t)len;
+    if (cnt) CC_CUDA(dev, cudaMemcpyAsync(dst, src->buf->plane[0], cnt * 4, cudaMemcpyDeviceToHost, dev->stream));
+    return CC_OK;
+}
+// pinned host memory for staging (async exports, weight uploads)
+extern "C" CC_API int cc_host_alloc(cc_device* dev, size_t bytes, void** out) {
+    if (!dev || !out) return CC_ERR_ARG;
+    CC_ENTER(dev);
+    CC_CUDA(dev, cudaMallocHost(out, bytes ? bytes : 1));
+    return CC_OK;
+}
+extern "C" CC_API void cc_host_free(cc_device* dev, void* p) {
+    if (!dev || !p) return;
+    CC_ENTER(dev);
+    cudaFreeHost(p);
 }
 
 // ---- matmul_vec: cpu_tensor.rs:371-386 + primitives/matmul_vec.rs:9-78 -------------------------------------------------

@@ -39,6 +39,8 @@
 //   Q8_K   qs  int8  [rows][k]            d   f32 [rows][k/256]
 // ------------------------------------------------------------------------------------------
 #define CC_MAX_PLANES 4
+#define CC_N_SLOTS 16
+#define CC_HISTORY_CAP 65536
 
 struct cc_device;
 
@@ -116,6 +118,10 @@ struct cc_device {
     size_t dev_idx_bytes = 0;
 
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;    // cc_bench_timer_*
+    // greedy decode without host round trips (capi.cu cc_argmax_to_slot / cc_copy_rows_from_slot): token-id slots and the history
+    // of sampled ids, both in device memory
+    int64_t* slots = nullptr;         // [CC_N_SLOTS]
+    int64_t* history = nullptr;       // [CC_HISTORY_CAP]
     unsigned* err_host = nullptr;     // host-mapped word a persistent kernel raises when one of its bounded spins times out (mega.cu)
 
     // debug tap
@@ -208,6 +214,8 @@ int cc_launch_silu(cc_device* dev, float* x, int64_t n);
 int cc_launch_gelu(cc_device* dev, float* x, int64_t n);
 int cc_launch_binary(cc_device* dev, float* x, int64_t n, const float* y, int64_t ny, int op);   // 0 add, 1 mul
 int cc_launch_scale(cc_device* dev, float* x, int64_t n, float s);
+int cc_launch_argmax(cc_device* dev, const float* x, int64_t n, int64_t* slot, int64_t* hist, const int64_t* hist_index_dev, int64_t hist_index);
+int cc_ensure_slots(cc_device* dev);
 int cc_launch_strided_copy(cc_device* dev, const void* src, int src_dtype, const int64_t* sshape,
                            const int64_t* sstrides, void* dst, int dst_dtype, const int64_t* dstrides,
                            int64_t dst_offset, int ndim);
@@ -217,8 +225,10 @@ int cc_launch_batch_matmul(cc_device* dev, const float* a, const void* b, int b_
 
 // ---- matvec_stream.cu --------------------------------------------------------------------------------
 struct StreamMats {           // up to 3 weight matrices sharing one activation (wq,wk,wv / gate,up)
-    const uint8_t* qs[3];
-    const uint16_t* d[3];
+    const uint8_t* qs[3];     // plane 0 (quants)
+    const uint16_t* d[3];     // plane 1 (Q8_0 / Q4_0: f16 scales)
+    const uint8_t* p2[3];     // planes 2 and 3 of the K-quant layouts (generic MATVEC phase of the megakernel)
+    const uint8_t* p3[3];
     float* out[3];
     int m[3];
     int n;
@@ -244,16 +254,19 @@ struct AttnArgs {            // fused decode attention (fused.cu)
 };
 struct DeqPlanes { const uint8_t* p[CC_MAX_PLANES]; int64_t cols; };
 // megakernel phase descriptor (mega.cu); built by lazy.cu
-enum { MK_NORMQ = 0, MK_MATVEC = 1, MK_ATTN = 2, MK_ROWS = 3, MK_REDUCE = 4, MK_GATHER = 5 };
+enum { MK_NORMQ = 0, MK_MATVEC = 1, MK_ATTN = 2, MK_ROWS = 3, MK_REDUCE = 4, MK_GATHER = 5, MK_ARGMAX = 6 };
 struct MkPhase {
     int type, wtype, write_back, next_matvec;
     int xgpu, red_n, next_matvec2, spare; float* red_dst; const float* red_res;   // cross-GPU barrier after this phase ; REDUCE/GATHER phase operands   // next_matvec / next_matvec2: index of the next MATVEC phase and of the one after it (look-ahead prefetch), -1 if none
     // NORMQ (and the output quantisation of ATTN)
     float* x; float* orig; const float* norm_w; float eps; int n; ActQ8_0 act;
+    int act_type, spare2;               // MATVEC: CC_Q8_0 (streaming phases) or CC_Q8_K (generic phases: K-quant weights)
     StreamArgs mv;                      // MATVEC
     AttnArgs at;                        // ATTN
     unsigned long long dyn_off, rope_off;   // ATTN {pos, kv_len} / ROWS row list ; RoPE table
     DeqPlanes planes; int src_dtype, dst_dtype, n_rows, pad; long long cols; void* dst;   // ROWS
+    const long long* rows_dev;          // ROWS: row indices in device memory (a token slot) instead of the dyn block ; ARGMAX: x = input, n = length,
+    long long* slot_dev; long long* hist_dev;   //   slot_dev / hist_dev = where the index goes (hist index at dyn_off, < 0: none)
 };
 size_t cc_mega_smem_for_phase(const MkPhase& ph);      // working area, without the norm-weight staging area on top of it
 const CommDev* cc_comm_dev(cc_device* dev);
@@ -264,7 +277,7 @@ int cc_launch_all_reduce(cc_device* dev, float* x, int64_t n, const float* resid
 int cc_launch_all_gather(cc_device* dev, const float* src, int64_t n, float* dst);
 extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase);
 int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem_work, size_t smem_wstage,
-                   unsigned long long* prof, const CommDev* comm);
+                   unsigned long long* prof, const CommDev* comm, bool generic);
 int cc_check_async_error(cc_device* dev);     // after a stream synchronize: did a persistent kernel give up on a barrier?
 int cc_launch_normq(cc_device* dev, float* x, float* orig, const float* norm_w, float eps, int64_t n, void* act_scratch, bool write_back);
 int cc_launch_attn_decode(cc_device* dev, const AttnArgs& a);
@@ -273,6 +286,7 @@ LazyState* cc_lazy_create(cc_device* dev);
 void cc_lazy_destroy(cc_device* dev);
 int cc_lazy_flush(cc_device* dev);
 bool cc_stream_supported(int type, int64_t k);
+bool cc_mega_generic_supported(int type, int64_t k);      // K-quant weights: generic MATVEC phase of the megakernel (mega.cu)
 int cc_launch_matvec_stream(cc_device* dev, int type, const StreamArgs& A);
 int cc_launch_matvec_stream_plain(cc_device* dev, const cc_buf* w, const void* act, float* out, int64_t m, int64_t k);
 

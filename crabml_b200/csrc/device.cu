@@ -108,6 +108,8 @@ extern "C" CC_API void cc_device_destroy(cc_device* dev) {
     if (dev->act_scratch) cudaFree(dev->act_scratch);
     if (dev->pinned) cudaFreeHost(dev->pinned);
     if (dev->err_host) cudaFreeHost(dev->err_host);
+    if (dev->slots) cudaFree(dev->slots);
+    if (dev->history) cudaFree(dev->history);
     if (dev->dev_idx) cudaFree(dev->dev_idx);
     cudaFree(dev->exp_lut);
     cudaFree(dev->gelu_lut);
@@ -190,6 +192,14 @@ int cc_new_activation(cc_device* dev, int64_t nelems, int dtype, bool zero, cc_b
     b->dev = dev; b->dtype = dtype; b->nelems = nelems; b->base = p; b->bytes = cls; b->pooled = true;
     b->plane[0] = (uint8_t*)p;
     *out = b;
+    return CC_OK;
+}
+
+int cc_ensure_slots(cc_device* dev) {
+    if (dev->slots) return CC_OK;
+    CC_CUDA(dev, cudaMalloc((void**)&dev->slots, CC_N_SLOTS * 8));
+    CC_CUDA(dev, cudaMemset(dev->slots, 0, CC_N_SLOTS * 8));
+    CC_CUDA(dev, cudaMalloc((void**)&dev->history, (size_t)CC_HISTORY_CAP * 8));
     return CC_OK;
 }
 

@@ -142,6 +142,19 @@ public:
         cc_view d = view(), s = src.view();
         check(dev_, cc_copy_rows_from(dev_, &d, &s, rows.data(), (int)rows.size()));
     }
+    // greedy decoding without a host round trip per token (extension of the C ABI, crabml_cuda.h)
+    void copy_rows_from_slot(const CudaTensor& src, int slot) {
+        cc_view d = view(), s = src.view();
+        check(dev_, cc_copy_rows_from_slot(dev_, &d, &s, slot));
+    }
+    void argmax_to_slot(int slot, int64_t hist_index) const {
+        cc_view v = view();
+        check(dev_, cc_argmax_to_slot(dev_, &v, slot, hist_index));
+    }
+    void export_async(float* dst, size_t n) const {
+        cc_view v = view();
+        check(dev_, cc_tensor_export_f32_async(dev_, &v, dst, n));
+    }
     void export_to(float* dst, size_t n) const {                                          // api.rs:52
         cc_view v = view();
         check(dev_, cc_tensor_export_f32(dev_, &v, dst, n));

@@ -1,7 +1,9 @@
 // llama2_runner.cpp -- replay of crabml-llama2's Llama2Runner<T> with T = CudaTensor.
 // The op ORDER is the reference's, verbatim (llama2.rs:184-281 forward/forward_llama, :527-603 attention,
 // :605-638 ffn); this file contains no arithmetic of its own.
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
@@ -19,7 +21,10 @@ struct ccr_runner {
     std::vector<CudaTensor> wq, wk, wv, wo, ffn_gate, ffn_down, ffn_up, rms_att, rms_ffn;
     std::vector<CudaTensor> key_cache, value_cache;       // (layer) x [n_kv_heads, seq, head_dim]
     std::vector<float> logits;
+    float* pinned_logits = nullptr;       // staging ring of the asynchronous logits export (generate_greedy_ex), grown on demand
+    size_t pinned_floats = 0;
     std::string last_error;
+    ~ccr_runner() { if (pinned_logits) cc_host_free(dev, pinned_logits); }
 
     // Sharded decode.  shard_world > 1: this process holds heads [rank*H/N, (rank+1)*H/N) of wq/wk/wv (rows), the
     // matching COLUMNS of wo, hidden_local rows of gate/up and columns of down, vocab/N rows of the classifier; the replay is
@@ -30,17 +35,18 @@ struct ccr_runner {
     int head_size() const { return conf.embedding_dim / conf.n_heads; }
     int64_t kv_cache_len() const { return key_cache[0].shape()[1]; }
 
-    CudaTensor forward_llama(const std::vector<int64_t>& tokens, int64_t pos);
+    CudaTensor forward_llama(const std::vector<int64_t>& tokens, int64_t pos, int slot = -1);
+    CudaTensor logits_tensor(CudaTensor x, int64_t n_batch);
+    void greedy_step(const int64_t* token, int64_t pos, int64_t hist_index, float* logits_async);
     CudaTensor forward_multi_query_attention(CudaTensor q, CudaTensor k, CudaTensor v, int l, int64_t n_batch);
     CudaTensor forward_ffn(CudaTensor x, int l);
     void forward(const std::vector<int64_t>& tokens, int64_t pos, float* logits_out);
 };
 
-// llama2.rs:184-211
-void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float* logits_out) {
-    CudaTensor x = forward_llama(tokens, pos);
+// llama2.rs:195-208: last row -> classifier (-> gather of the vocab/N slices on the sharded path)
+CudaTensor ccr_runner::logits_tensor(CudaTensor x, int64_t n_batch) {
     CudaTensor x_final = CudaTensor::alloc({conf.embedding_dim}, CC_F32, dev);
-    x_final.copy_rows_from(x, {(int64_t)tokens.size() - 1});
+    x_final.copy_rows_from(x, {n_batch - 1});
     const CudaTensor& ow = output_weight.valid() ? output_weight : token_embed;
     CudaTensor lg = ow.matmul_vec(x_final);
     if (world() > 1) {                                   // row-split classifier: gather the vocab/N slices
@@ -48,19 +54,36 @@ void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float*
         full.all_gather_from(lg);
         lg = std::move(full);
     }
+    return lg;
+}
+
+// llama2.rs:184-211
+void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float* logits_out) {
+    CudaTensor lg = logits_tensor(forward_llama(tokens, pos), (int64_t)tokens.size());
     if (logits_out) lg.export_to(logits_out, (size_t)conf.vocab_size);
     else CudaTensor::check(dev, cc_device_flush(dev));     // lazy mode: submit this token's work without a host sync
 }
 
+// One decode step whose sampled token never visits the host: forward (token from the host, or -- token == nullptr -- from device slot 0),
+// greedy argmax (sampler.rs:109-116) into slot 0 and the device-side history; optionally the logits are exported WITHOUT waiting.
+void ccr_runner::greedy_step(const int64_t* token, int64_t pos, int64_t hist_index, float* logits_async) {
+    CudaTensor x = token ? forward_llama({*token}, pos) : forward_llama({0}, pos, 0);
+    CudaTensor lg = logits_tensor(std::move(x), 1);
+    lg.argmax_to_slot(0, hist_index);
+    if (logits_async) lg.export_async(logits_async, (size_t)conf.vocab_size);     // flushes (asynchronously) as well
+    else CudaTensor::check(dev, cc_device_flush(dev));
+}
+
 // llama2.rs:213-281
-CudaTensor ccr_runner::forward_llama(const std::vector<int64_t>& tokens, int64_t pos) {
+CudaTensor ccr_runner::forward_llama(const std::vector<int64_t>& tokens, int64_t pos, int slot) {
     const int64_t embed_dim = conf.embedding_dim, n_heads = local_heads(), n_kv_heads = local_kv_heads();
     const int64_t head_dim = head_size();
     const int64_t rope_dim = conf.rope_dim > 0 ? conf.rope_dim : head_dim;
     const int64_t n_batch = (int64_t)tokens.size();
 
     CudaTensor x = CudaTensor::alloc({n_batch, embed_dim}, CC_F32, dev);
-    x.copy_rows_from(token_embed, tokens);
+    if (slot >= 0) x.copy_rows_from_slot(token_embed, slot);      // the id sampled on the device by the previous step
+    else x.copy_rows_from(token_embed, tokens);
 
     for (int l = 0; l < conf.n_layers; l++) {
         CudaTensor x_attn_orig = x.dup();
@@ -206,26 +229,52 @@ extern "C" CC_API int ccr_runner_forward(ccr_runner* r, const int64_t* tokens, i
     return guarded(r, [&] { r->forward(std::vector<int64_t>(tokens, tokens + n_tokens), pos, logits_out); });
 }
 
+// Greedy decode loop (prefill + generate with temperature 0: llama2.rs:111-172, sampler.rs:109-116).  Sampling runs on the device
+// and the sampled id feeds the next step from a device slot, so no step waits for the host:
+//   eos_token < 0  : all steps are submitted back to back, the ids come back in one copy at the end
+//   eos_token >= 0 : the id of every step is read back (8 bytes) before the next step is submitted, to stop at EOS exactly like
+//                    the reference (the KV cache must not grow past it)
+// logits_out (optional, steps x vocab floats): the logits of every generated position, exported asynchronously through a pinned
+// staging ring -- what a host-side sampler would consume.
+extern "C" CC_API int ccr_runner_generate_greedy_ex(ccr_runner* r, const int64_t* prompt, int32_t n_prompt, int32_t steps,
+                                                    int64_t eos_token, int64_t* out_tokens, int32_t* n_out, float* logits_out) {
+    if (!r || !prompt || n_prompt < 1 || !out_tokens || !n_out || steps < 1) return CC_ERR_ARG;
+    *n_out = 0;
+    float* pinned = nullptr;
+    return guarded(r, [&] {
+        const size_t vocab = (size_t)r->conf.vocab_size;
+        int64_t pos = r->kv_cache_len();
+        // how many tokens may be generated: the first comes from the prompt pass, the rest are bounded by the context (llama2.rs:141-147)
+        const int64_t max_seq = r->conf.seq_len - (pos + n_prompt) - 1;
+        const int64_t total = 1 + std::max<int64_t>(0, std::min<int64_t>(max_seq, (int64_t)steps - 1));
+        if (logits_out) {
+            if (r->pinned_floats < (size_t)total * vocab) {
+                if (r->pinned_logits) { CudaTensor::check(r->dev, cc_device_synchronize(r->dev)); cc_host_free(r->dev, r->pinned_logits); r->pinned_logits = nullptr; r->pinned_floats = 0; }
+                CudaTensor::check(r->dev, cc_host_alloc(r->dev, (size_t)total * vocab * 4, (void**)&r->pinned_logits));
+                r->pinned_floats = (size_t)total * vocab;
+            }
+            pinned = r->pinned_logits;
+        }
+        for (int i = 0; i + 1 < n_prompt; i++) r->forward({prompt[i]}, pos++, nullptr);
+        r->greedy_step(&prompt[n_prompt - 1], pos++, 0, pinned);
+        int64_t done = 1;
+        if (eos_token < 0) {
+            for (; done < total; done++) r->greedy_step(nullptr, pos++, done, pinned ? pinned + (size_t)done * vocab : nullptr);
+            CudaTensor::check(r->dev, cc_read_history(r->dev, 0, done, out_tokens));
+        } else {
+            CudaTensor::check(r->dev, cc_read_history(r->dev, 0, 1, out_tokens));
+            for (; done < total; done++) {
+                r->greedy_step(nullptr, pos++, done, pinned ? pinned + (size_t)done * vocab : nullptr);
+                CudaTensor::check(r->dev, cc_read_history(r->dev, done, 1, out_tokens + done));
+                if (out_tokens[done] == eos_token) break;          // the reference returns before yielding EOS (llama2.rs:160-163)
+            }
+        }
+        *n_out = (int32_t)done;
+        if (logits_out) { CudaTensor::check(r->dev, cc_device_synchronize(r->dev)); std::memcpy(logits_out, pinned, (size_t)done * vocab * 4); }
+    });
+}
+
 extern "C" CC_API int ccr_runner_generate_greedy(ccr_runner* r, const int64_t* prompt, int32_t n_prompt, int32_t steps,
                                                  int64_t eos_token, int64_t* out_tokens, int32_t* n_out) {
-    if (!r || !prompt || n_prompt < 1 || !out_tokens || !n_out) return CC_ERR_ARG;
-    *n_out = 0;
-    return guarded(r, [&] {
-        // prefill: one forward per prompt token (llama2.rs:127-129), then sample
-        int64_t base_pos = r->kv_cache_len();
-        for (int i = 0; i < n_prompt; i++) r->forward({prompt[i]}, base_pos + i, r->logits.data());
-        int64_t token = sample_argmax(r->logits);
-        int64_t pos = r->kv_cache_len();
-        // generate (llama2.rs:141-172): the first token comes from prefill
-        int64_t max_seq = r->conf.seq_len - pos - 1;
-        int64_t max_steps = std::min<int64_t>(max_seq, (int64_t)steps - 1);
-        out_tokens[(*n_out)++] = token;
-        for (int64_t p = pos; p < pos + max_steps; p++) {
-            r->forward({token}, p, r->logits.data());
-            int64_t nt = sample_argmax(r->logits);
-            if (nt == eos_token) return;
-            token = nt;
-            out_tokens[(*n_out)++] = token;
-        }
-    });
+    return ccr_runner_generate_greedy_ex(r, prompt, n_prompt, steps, eos_token, out_tokens, n_out, nullptr);
 }

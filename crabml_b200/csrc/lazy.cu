@@ -21,7 +21,7 @@
 
 #include "common.cuh"
 
-enum LKind { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU, L_ALLREDUCE, L_ALLGATHER };
+enum LKind { L_COPY_ROWS, L_DUP, L_RMS_NORM, L_MUL, L_ADD, L_SCALE, L_MATVEC, L_ROPE, L_CONCAT, L_CONTIGUOUS, L_BMM, L_SOFTMAX, L_SILU, L_GELU, L_ALLREDUCE, L_ALLGATHER, L_ARGMAX };
 
 struct LView { cc_buf* buf = nullptr; int ndim = 0; int64_t shape[CC_MAX_DIMS] = {0, 0, 0, 0}, strides[CC_MAX_DIMS] = {0, 0, 0, 0}; };
 
@@ -140,6 +140,7 @@ struct Plan {
     std::vector<MkPhase> phases;     // megakernel form of the same plan (valid while mega_ok)
     bool mega_ok = true;
     size_t mega_smem = 1024, mega_wstage = 0;
+    bool mega_generic = false;       // some MATVEC phase is generic (K-quant weights): launch the instantiation that carries that code
     void S(uint64_t v) { sig.push_back(v); }
     void SP(const void* p) { sig.push_back((uint64_t)(uintptr_t)p); }
     size_t dyn_put(const void* p, size_t n) {
@@ -184,8 +185,9 @@ struct Fuser {
     static bool same_dense_1xN(const LView& v, int64_t n) { return vcontig(v) && vlen(v) == n; }
 
     // ---- eager fallback for one op -----------------------------------------------------------------------------
+    bool covered_by_phase = false;     // set while try_generic emits the eager steps of ops its megakernel phase covers
     void fallback(size_t i) {
-        P.mega_ok = false;
+        if (!covered_by_phase) P.mega_ok = false;
         LOp op = q[i];       // copy: lambdas outlive the queue only until flush ends, but keep them self-contained
         cc_device* d = dev;
         P.S(0x1000 + op.kind); P.SP(op.a.buf ? op.a.buf->plane[0] : nullptr); P.SP(op.b.buf ? op.b.buf->plane[0] : nullptr);
@@ -215,6 +217,7 @@ struct Fuser {
             case L_GELU: return cc_launch_gelu(d, (float*)a.buf->plane[0], vlen(a));
             case L_ALLREDUCE: return cc_launch_all_reduce(d, (float*)a.buf->plane[0], op.i0, nullptr);
             case L_ALLGATHER: return cc_launch_all_gather(d, (const float*)b.buf->plane[0], op.i0, (float*)a.buf->plane[0]);
+            case L_ARGMAX: return cc_launch_argmax(d, (const float*)a.buf->plane[0], vlen(a), d->slots + op.i0, d->history, nullptr, op.i1);
             case L_SOFTMAX: { int64_t cols = a.shape[a.ndim - 1]; return cc_launch_softmax(d, (float*)a.buf->plane[0], cols ? vlen(a) / cols : 0, cols); }
             case L_ROPE: return cc_launch_rope_exact(d, (float*)a.buf->plane[0], op.i1, op.i2, a.shape[a.ndim - 1], (int)op.f, op.i0, op.rows[0]);
             case L_CONCAT:
@@ -402,6 +405,7 @@ struct Fuser {
         A.q = (const float*)qb->plane[0]; A.k = (const float*)kb->plane[0]; A.v = (const float*)vb->plane[0];
         A.kcache = kc->plane[0]; A.vcache = vc->plane[0];
         A.out = (float*)b2.out->base;
+        if (*quantized && is(i + 9, L_MATVEC) && !cc_stream_supported(q[i + 9].a.buf->dtype, q[i + 9].a.shape[1])) *quantized = false;   // K-quant wo quantises (Q8_K) itself
         A.act_scratch = *quantized ? lz->act[1] : nullptr;
         A.n_heads = (int)n_heads; A.n_kv = (int)n_kv; A.hd = (int)hd; A.rope_dim = (int)rope_dim;
         A.max_len = (int)(seq_stride / hd); A.kv_f16 = kc->dtype == CC_F16;
@@ -428,17 +432,100 @@ struct Fuser {
         if (!is(i, L_COPY_ROWS)) return 0;
         const LOp& op = q[i];
         cc_device* d = dev;
-        size_t off = P.dyn_put(op.rows.data(), op.rows.size() * 8);
         const cc_buf* src = op.b.buf;
         void* dst = op.a.buf->plane[0];
-        int dt = op.a.buf->dtype, n = (int)op.rows.size();
+        int dt = op.a.buf->dtype;
         int64_t cols = op.a.shape[op.a.ndim - 1];
-        P.S(0x2005); P.SP(src->plane[0]); P.SP(dst); P.S(dt); P.S(n); P.S(cols); P.S(off);
-        P.steps.push_back([=](uint8_t* dyn_dev) { return cc_launch_dequant_rows(d, src, (const int64_t*)(dyn_dev + off), n, cols, dst, dt); });
+        const int slot = (int)op.i2 - 1;                     // >= 0: the single row index lives in a device slot (cc_copy_rows_from_slot)
+        int n = slot >= 0 ? 1 : (int)op.rows.size();
+        size_t off = slot >= 0 ? 0 : P.dyn_put(op.rows.data(), op.rows.size() * 8);
+        const int64_t* rows_dev = slot >= 0 ? dev->slots + slot : nullptr;
+        P.S(0x2005); P.SP(src->plane[0]); P.SP(dst); P.S(dt); P.S(n); P.S(cols); P.S(off); P.SP(rows_dev);
+        P.steps.push_back([=](uint8_t* dyn_dev) { return cc_launch_dequant_rows(d, src, rows_dev ? rows_dev : (const int64_t*)(dyn_dev + off), n, cols, dst, dt); });
         { MkPhase ph = {}; ph.type = MK_ROWS; ph.dyn_off = off; for (int t = 0; t < CC_MAX_PLANES; t++) ph.planes.p[t] = src->plane[t];
-          ph.planes.cols = src->cols > 0 ? src->cols : cols; ph.src_dtype = src->dtype; ph.dst_dtype = dt; ph.n_rows = n; ph.cols = cols; ph.dst = dst; P.phases.push_back(ph); }
+          ph.planes.cols = src->cols > 0 ? src->cols : cols; ph.src_dtype = src->dtype; ph.dst_dtype = dt; ph.n_rows = n; ph.cols = cols; ph.dst = dst;
+          ph.rows_dev = (const long long*)rows_dev; P.phases.push_back(ph); }
         q[i].done = true;
         return 1;
+    }
+
+    // ---- pattern: greedy sampling on the device (cc_argmax_to_slot): the history index travels in dyn ------------------------------------------------
+    size_t try_argmax(size_t i) {
+        if (!is(i, L_ARGMAX)) return 0;
+        const LOp& op = q[i];
+        cc_device* d = dev;
+        const float* x = (const float*)op.a.buf->plane[0];
+        const int64_t n = vlen(op.a);
+        int64_t* slot = dev->slots + op.i0;
+        int64_t* hist = dev->history;
+        const int64_t hidx = op.i1;
+        size_t off = P.dyn_put(&hidx, 8);
+        P.S(0x2007); P.SP(x); P.S((uint64_t)n); P.SP(slot); P.S(off);
+        P.steps.push_back([=](uint8_t* dyn_dev) { return cc_launch_argmax(d, x, n, slot, hist, (const int64_t*)(dyn_dev + off), -1); });
+        { MkPhase ph = {}; ph.type = MK_ARGMAX; ph.x = (float*)x; ph.n = (int)n; ph.dyn_off = off; ph.slot_dev = (long long*)slot; ph.hist_dev = (long long*)hist; P.phases.push_back(ph); }
+        q[i].done = true;
+        return 1;
+    }
+
+    // ---- pattern: K-quant matvecs (generic MATVEC phase of the megakernel) ----------------------------------------------------------------
+    //   [[DUP] RMS_NORM MUL]  MATVEC{1..3, same K-quant type, same f32 row x, b = 1}  [SILU MUL | ADD]
+    // In the CUDA-graph mode (lazy = 1) these ops keep running as their eager kernels, in order (fallback steps); for the megakernel
+    // the whole group is ONE phase: fused prologue (norm + Q8_K quantisation of x) + T::row_dot rows + epilogue -- the same
+    // arithmetic as the eager kernels, so the two modes agree bit for bit.
+    size_t try_generic(size_t i) {
+        size_t j = i;
+        cc_buf* orig = nullptr; cc_buf* xb = nullptr;
+        const float* norm_w = nullptr; float eps = 0.0f;
+        if (is(j, L_DUP) && is(j + 1, L_RMS_NORM) && q[j + 1].a.buf == q[j].a.buf) { orig = q[j].out; j++; }
+        if (is(j, L_RMS_NORM) && is(j + 1, L_MUL) && q[j + 1].a.buf == q[j].a.buf) {
+            const LOp &rn = q[j], &mu = q[j + 1];
+            const int64_t n = vlen(rn.a);
+            if (rn.a.ndim > 2 || (rn.a.ndim == 2 && rn.a.shape[0] != 1) || !vcontig(rn.a)) return 0;
+            if (vlen(mu.b) != n || mu.b.buf->dtype != CC_F32 || !vcontig(mu.b)) return 0;
+            xb = rn.a.buf; norm_w = (const float*)mu.b.buf->plane[0]; eps = rn.f;
+            j += 2;
+        } else if (orig) return 0;
+        if (!is(j, L_MATVEC)) return 0;
+        const LOp& m0 = q[j];
+        const int wt = m0.a.buf->dtype;
+        const int64_t k = m0.a.shape[1];
+        if (!cc_mega_generic_supported(wt, k)) return 0;
+        if (!xb) xb = m0.b.buf;
+        if (m0.b.buf != xb || xb->dtype != CC_F32 || vlen(m0.b) != k || !vcontig(m0.b) || (m0.b.ndim == 2 && m0.b.shape[0] != 1) || m0.b.ndim > 2) return 0;
+        size_t n = 1;
+        while (n < 3 && is(j + n, L_MATVEC) && q[j + n].b.buf == xb && q[j + n].a.buf->dtype == wt && q[j + n].a.shape[1] == k && vlen(q[j + n].b) == k) n++;
+        StreamArgs A = {};
+        A.k = (int)k; A.exp_lut = dev->exp_lut;
+        size_t used_mv = n;
+        if (n >= 2 && is(j + 2, L_SILU) && is(j + 3, L_MUL) && q[j + 2].a.buf == q[j].out && q[j + 3].a.buf == q[j].out && q[j + 3].b.buf == q[j + 1].out &&
+            q[j].a.shape[0] == q[j + 1].a.shape[0] && vlen(q[j + 3].b) == q[j].a.shape[0] && dead_after(q[j + 1].out, j + 4)) {
+            n = 2; A.epilogue = 2; used_mv = 4;
+        } else if (n == 1 && is(j + 1, L_ADD) && q[j + 1].a.buf == m0.out && vlen(q[j + 1].b) == m0.a.shape[0] && q[j + 1].b.buf->dtype == CC_F32 && vcontig(q[j + 1].b) &&
+                   q[j + 1].b.buf != xb) {
+            A.epilogue = 1; A.residual = (const float*)q[j + 1].b.buf->plane[0]; used_mv = 2;
+        } else if (n > 1 && is(j + n, L_SILU)) { n = 1; used_mv = 1; }
+        if (is(j + used_mv, L_ALLREDUCE) || is(j + used_mv, L_ALLGATHER)) return 0;      // sharded K-quant models run in the CUDA-graph mode
+        const size_t end = j + used_mv;
+        // the normalised row is overwritten in place by the eager ops; the fused prologue never materialises it: nobody else may read it
+        if (norm_w && !dead_after(xb, end)) return 0;
+        A.mats.n = (int)n;
+        for (size_t t = 0; t < n; t++) {
+            const cc_buf* w = q[j + t].a.buf;
+            if (w->cols != k) return 0;
+            A.mats.qs[t] = w->plane[0]; A.mats.d[t] = (const uint16_t*)w->plane[1]; A.mats.p2[t] = w->plane[2]; A.mats.p3[t] = w->plane[3];
+            A.mats.out[t] = (float*)q[j + t].out->base;
+            A.mats.m[t] = (int)q[j + t].a.shape[0];
+        }
+        MkPhase ph = {};
+        ph.type = MK_MATVEC; ph.wtype = wt; ph.act_type = CC_Q8_K; ph.mv = A;
+        ph.x = (float*)xb->plane[0]; ph.orig = orig ? (float*)orig->base : nullptr; ph.norm_w = norm_w; ph.eps = eps; ph.n = (int)k;
+        // eager steps for the CUDA-graph mode, op by op, without disqualifying the megakernel form
+        covered_by_phase = true;
+        for (size_t t = i; t < end; t++) fallback(t);
+        covered_by_phase = false;
+        P.phases.push_back(ph);
+        P.mega_generic = true;
+        return end - i;
     }
 
     // megakernel only: phases[at] = NORMQ (not write-back) directly followed by its single MATVEC consumer -> one MATVEC
@@ -467,6 +554,8 @@ struct Fuser {
             size_t used;
             cc_buf* xb = nullptr;
             if ((used = try_copy_rows(i))) { i += used; continue; }
+            if ((used = try_argmax(i))) { i += used; continue; }
+            if ((used = try_generic(i))) { i += used; continue; }
             if ((used = try_normq(i, 0, &xb))) {
                 i += used;
                 // every following group of matvecs on the normalised x reuses scratch 0
@@ -588,7 +677,7 @@ int cc_lazy_flush(cc_device* dev) {
             if (!rc) {
                 if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue + 1024 * (ph.mv.k >> 10) : 0)); }
                 rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem, P.mega_wstage,
-                                               P.phases.size() < 4000 ? lz->prof_dev : nullptr, cc_comm_dev(dev)) : run_steps(lz->dyn_dev);
+                                               P.phases.size() < 4000 ? lz->prof_dev : nullptr, cc_comm_dev(dev), P.mega_generic) : run_steps(lz->dyn_dev);
                 e = cudaStreamEndCapture(dev->stream, &graph);
                 if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: end capture: %s", cudaGetErrorString(e));
             }

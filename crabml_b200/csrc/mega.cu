@@ -18,6 +18,8 @@
 
 #include "common.cuh"
 #include "dequant.cuh"
+#include "quantize_dev.cuh"
+#include "vecdot.cuh"
 
 // one CTA of 16 warps per SM: the grid barrier has 148 participants instead of 296 (its cost is what bounds a phase)
 #define MK_THREADS 512
@@ -472,7 +474,100 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
     flush_pending();
     // this warp is done: its register stages are free, so it requests its first segments of the next MATVEC phase right away instead
     // of idling until the slowest warp of the CTA reaches the barrier (the tail of a phase becomes prefetch time)
-    if (early_next) { if (early_next[0].wtype == CC_Q8_0) matvec_prefetch<CC_Q8_0>(early_next[0].mv, P); else matvec_prefetch<CC_Q4_0>(early_next[0].mv, P); }
+    if (early_next) { if (early_next[0].wtype == CC_Q8_0) matvec_prefetch<CC_Q8_0>(early_next[0].mv, P); else if (early_next[0].wtype == CC_Q4_0) matvec_prefetch<CC_Q4_0>(early_next[0].mv, P); }
+}
+
+// ---- generic MATVEC phase: K-quant weights (Q2_K .. Q6_K, Q8_K) against the Q8_K-quantised activation ---------------------------
+// Same shape as phase_matvec -- fused prologue ([rms_norm * w] + activation quantisation, recomputed by every CTA), rows dealt
+// warp-major, the same epilogues -- but the row dot is the type's T::row_dot of vecdot.cuh (what the eager matvec_kernel runs, hence
+// the same bits) and the weights are not pipelined through registers across phase boundaries.
+// shared memory: qs [k] | d [k/256] | bsums [k/16] (TKBase) | reduction scratch | f32 x
+__device__ __forceinline__ int mk_generic_sx_offset(int k) { return ((TKBase::smem_bytes(k) + 15) & ~15) + 256; }
+template <class T>
+__device__ void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, bool x_staged, const uint16_t* exp_lut, unsigned long long* stamp1) {
+    const StreamArgs& A = ph.mv;
+    const StreamMats& M = A.mats;
+    const int k = A.k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int8_t* s_q = (int8_t*)smem;
+    float* s_d = (float*)(smem + al16i(k));
+    int16_t* s_bs = (int16_t*)(smem + al16i(k) + al16i(k / 256 * 4));
+    float* s_red = (float*)(smem + mk_generic_sx_offset(k) - 256);
+    float* s_x = (float*)(smem + mk_generic_sx_offset(k));
+    {   // one L2 round trip: the f32 row (unless requested right after the barrier) and the norm weights (unless staged before it)
+        const int n4 = k >> 2;
+        const unsigned sx = (unsigned)__cvta_generic_to_shared(s_x), sw = (unsigned)__cvta_generic_to_shared(s_w);
+        if (ph.norm_w && !w_staged)
+            for (int i = threadIdx.x; i < n4; i += MK_THREADS) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sw + i * 16), "l"(ph.norm_w + i * 4) : "memory");
+        if (!x_staged)
+            for (int i = threadIdx.x; i < n4; i += MK_THREADS) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 16), "l"(ph.x + i * 4) : "memory");
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (stamp1) stamp1[3] = globaltimer_ns();
+    }
+    float rms = 1.0f;
+    if (ph.norm_w) {                                                    // canonical order (common.cuh)
+        float ss = 0.0f;
+        const float4* x4 = (const float4*)s_x;
+        for (int i = threadIdx.x; i < (k >> 2); i += MK_THREADS) ss += cc_sq4(x4[i]);
+        rms = sqrtf(cc_block_sum_512(ss, s_red) / (float)k + ph.eps);
+    }
+    if (stamp1) stamp1[4] = globaltimer_ns();
+    if (ph.orig && blockIdx.x == 0)                                     // Tensor::dup of the un-normalised row (llama2.rs:227,607)
+        for (int i = threadIdx.x; i < (k >> 2); i += MK_THREADS) ((float4*)ph.orig)[i] = ((const float4*)s_x)[i];
+    for (int sb = warp; sb < (k >> 8); sb += MK_WARPS) {                // one warp per 256-element super-block (buf_q8_k.rs:84-131)
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = s_x[sb * 256 + lane * 8 + i];
+            if (ph.norm_w) v[i] = (v[i] / rms) * s_w[sb * 256 + lane * 8 + i];
+        }
+        cc_quant_q8k_sblock(v, lane, s_q + sb * 256, s_d + sb, s_bs + sb * 16);
+    }
+    __syncthreads();
+    if (stamp1) *stamp1 = globaltimer_ns();
+    // rows: the same warp-major dealing and epilogues as phase_matvec
+    const int gw = warp * gridDim.x + blockIdx.x, TW = gridDim.x * MK_WARPS;
+    const bool pair = A.epilogue == 2;
+    const int m_cat = pair ? M.m[0] : M.m[0] + (M.n > 1 ? M.m[1] : 0) + (M.n > 2 ? M.m[2] : 0);
+    const int n_rows = gw < m_cat ? (m_cat - gw + TW - 1) / TW : 0;
+    const int n_vrows = pair ? 2 * n_rows : n_rows;
+    float first = 0.0f, pend_a = 0.0f, pend_b = 0.0f, pend_res = 0.0f;
+    unsigned short pend_lut = 0;
+    int pend_row = -1;
+    auto flush_pending = [&]() {
+        if (lane == 0 && pend_row >= 0) {
+            if (pair) M.out[0][pend_row] = (pend_a / (1.0f + h2f_bits(pend_lut))) * pend_b;
+            else M.out[0][pend_row] = pend_a + pend_res;
+        }
+        pend_row = -1;
+    };
+    for (int i = 0; i < n_vrows; i++) {
+        int mat = 0, r;
+        if (pair) { mat = i & 1; r = gw + (i >> 1) * TW; }
+        else {
+            r = gw + i * TW;
+            if (M.n > 1 && r >= M.m[0]) { r -= M.m[0]; mat = 1; if (M.n > 2 && r >= M.m[1]) { r -= M.m[1]; mat = 2; } }
+        }
+        WPlanes W;
+        W.p[0] = mat == 0 ? M.qs[0] : mat == 1 ? M.qs[1] : M.qs[2];
+        W.p[1] = (const uint8_t*)(mat == 0 ? M.d[0] : mat == 1 ? M.d[1] : M.d[2]);
+        W.p[2] = mat == 0 ? M.p2[0] : mat == 1 ? M.p2[1] : M.p2[2];
+        W.p[3] = mat == 0 ? M.p3[0] : mat == 1 ? M.p3[1] : M.p3[2];
+        const float v = warp_sum(T::row_dot(W, r, k, smem, lane));
+        if (pair) {
+            if ((i & 1) == 0) { first = v; continue; }
+            flush_pending();
+            if (lane == 0) { pend_a = first; pend_b = v; pend_row = r; pend_lut = exp_lut[f2h_bits(-first)]; }
+        } else if (A.epilogue == 1) {
+            flush_pending();
+            if (lane == 0) { pend_a = v; pend_row = r; pend_res = ldcg_f(A.residual + r); }
+        } else if (lane == 0) {
+            float* o = mat == 0 ? M.out[0] : mat == 1 ? M.out[1] : M.out[2];
+            o[r] = v;
+        }
+    }
+    flush_pending();
 }
 
 // ---- ATTN phase: arithmetic of fused.cu attn_decode_kernel, heads dealt to CTAs.  The K (then V) rows of the head are
@@ -636,7 +731,7 @@ __device__ void phase_attn(const MkPhase& ph, float* sm, float* s_red, const uin
 
 // ---- ROWS phase: copy_rows_from with the row indices in dyn (embedding lookup / row pick) -----------------------------------
 __device__ void phase_rows(const MkPhase& ph, const uint8_t* dyn) {
-    const int64_t* rows = (const int64_t*)(dyn + ph.dyn_off);
+    const int64_t* rows = ph.rows_dev ? (const int64_t*)ph.rows_dev : (const int64_t*)(dyn + ph.dyn_off);      // a device slot: read through L2 (written by a previous launch)
     const int64_t total = (int64_t)ph.n_rows * ph.cols;
     for (int64_t i = (int64_t)blockIdx.x * MK_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * MK_THREADS) {
         const int64_t r = i / ph.cols, c = i - r * ph.cols;
@@ -647,6 +742,31 @@ __device__ void phase_rows(const MkPhase& ph, const uint8_t* dyn) {
         else v = dequant_elem(ph.src_dtype, ph.planes, e);
         if (ph.dst_dtype == CC_F32) ((float*)ph.dst)[i] = v; else ((__half*)ph.dst)[i] = __float2half_rn(v);
     }
+}
+
+// ---- ARGMAX phase: greedy sampling on the device (ops.cu argmax_kernel, the LAST maximum: sampler.rs:109-116); CTA 0 only -----------------
+__device__ void phase_argmax(const MkPhase& ph, const uint8_t* dyn, float* s_red) {
+    if (blockIdx.x != 0) return;
+    __shared__ long long s_idx[MK_WARPS];
+    const float* x = ph.x;
+    float bv = 0.0f; long long bi = -1;
+    for (long long i = threadIdx.x; i < ph.n; i += MK_THREADS) { const float v = ldcg_f(x + i); if (bi < 0 || !(v < bv)) { bv = v; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = bv; s_idx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < MK_WARPS; w++) { const float ov = s_red[w]; const long long oi = s_idx[w]; if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; } }
+        if (bi < 0) bi = 0;
+        *ph.slot_dev = bi;
+        const long long h = *(const long long*)(dyn + ph.dyn_off);
+        if (h >= 0 && h < CC_HISTORY_CAP) ph.hist_dev[h] = bi;
+    }
+    __syncthreads();
 }
 
 // ---- REDUCE / GATHER phases: second half of an exchange (the first half is epilogue 3 of the MATVEC phase + the handshake
@@ -686,6 +806,9 @@ __device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsigned xs
 #define MK_F_EARLY 32          // a warp requests its first segments of the next MATVEC phase as soon as IT has finished its rows
 #define MK_TYPE_CALL(T, CALL_Q8, CALL_Q4) do { if ((T) == CC_Q8_0) { CALL_Q8; } else { CALL_Q4; } } while (0)
 
+// GEN: the phase table contains generic (K-quant) MATVEC phases.  The streaming-only instantiation carries none of their code, so
+// its register allocation (the weight pipe lives in registers across phases) is not disturbed by them.
+template <bool GEN>
 __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const MkPhase* __restrict__ phases, int n_phases, const uint8_t* dyn,
                                                                          unsigned* bar, const uint16_t* exp_lut, unsigned long long* prof, int flags, int wtop_off,
                                                                          unsigned* err_host, const CommDev comm) {
@@ -726,7 +849,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         // an L2 round trip (in-order issue) before it could issue the phase's own loads.
         static_assert(sizeof(MkPhase) / 4 <= MK_THREADS, "descriptor does not fit one word per thread");
         const int nx = s_ph.next_matvec, nx2 = s_ph.next_matvec2;
-        const bool look = (flags & MK_F_LOOK) && nx > p && nx < n_phases && prefetched != nx && p + 1 < n_phases;
+        const bool look = (flags & MK_F_LOOK) && nx > p && nx < n_phases && prefetched != nx && p + 1 < n_phases;     // (the next MATVEC may turn out generic: checked below)
         int desc_w = 0, next_w = 0;
         if (p + 1 < n_phases && threadIdx.x < sizeof(MkPhase) / 4) desc_w = ((const int*)(phases + p + 1))[threadIdx.x];
         if (look && threadIdx.x < 128) {
@@ -746,6 +869,18 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         switch (s_ph.type) {
         case MK_NORMQ: phase_normq(s_ph, s_red); break;
         case MK_MATVEC:
+            if (GEN && s_ph.act_type == CC_Q8_K) {   // K-quant weights: generic phase, no register look-ahead
+                unsigned long long* st1 = stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr;
+                switch (s_ph.wtype) {
+                case CC_Q2_K: phase_matvec_generic<TQ2_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
+                case CC_Q3_K: phase_matvec_generic<TQ3_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
+                case CC_Q4_K: phase_matvec_generic<TQ45_K<false>>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
+                case CC_Q5_K: phase_matvec_generic<TQ45_K<true>>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
+                case CC_Q6_K: phase_matvec_generic<TQ6_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
+                default: phase_matvec_generic<TQ8_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
+                }
+                break;
+            }
             if (prefetched != p) MK_TYPE_CALL(s_ph.wtype, matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe), matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe));
             early = look && (flags & MK_F_EARLY);
             MK_TYPE_CALL(s_ph.wtype,
@@ -760,6 +895,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         case MK_ROWS: phase_rows(s_ph, dyn); break;
         case MK_REDUCE: phase_reduce(s_ph, comm, xseq, false); break;
         case MK_GATHER: phase_reduce(s_ph, comm, xseq, true); break;
+        case MK_ARGMAX: phase_argmax(s_ph, dyn, s_red); break;
         }
         if (stamp) prof[p * MK_PROF_SLOTS + 2] = globaltimer_ns();
         if (p + 1 < n_phases && threadIdx.x < sizeof(MkPhase) / 4) ((int*)&s_phs[(p + 1) & 1])[threadIdx.x] = desc_w;
@@ -776,8 +912,9 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         if ((flags & MK_F_TESTSTALL) && p == 2 && blockIdx.x == gridDim.x - 1) return;
         if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg);       // its bar.sync also publishes s_next (written just above)
         if (look) {
-            if (!early) MK_TYPE_CALL(s_next[0].wtype, matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe), matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe));
-            prefetched = nx;
+            const bool next_stream = s_next[0].wtype == CC_Q8_0 || s_next[0].wtype == CC_Q4_0;
+            if (!early && next_stream) MK_TYPE_CALL(s_next[0].wtype, matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe), matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe));
+            if (next_stream) prefetched = nx;
             if ((flags & MK_F_WSTAGE) && s_next[0].norm_n > 0) {     // immutable norm weights of the next fused prologue: one L2 trip less after the barrier
                 const unsigned sw = (unsigned)__cvta_generic_to_shared(s_w);
                 const float* nw = s_next[0].norm_w;
@@ -797,7 +934,8 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             const MkPhase& nph = s_phs[(p + 1) & 1];
             if ((flags & MK_F_XEARLY) && nph.type == MK_MATVEC && nph.x && !nph.red_n) {
                 const int nb = nph.mv.k >> 5, nbp = ((((nb + 31) >> 5) + MK_SEG - 1) / MK_SEG) * MK_SEG * 32;
-                const unsigned sx = (unsigned)__cvta_generic_to_shared(work + (size_t)nbp * 40 + 256);      // = s_x of phase_matvec's prologue
+                const size_t xoff = nph.act_type == CC_Q8_K ? (size_t)mk_generic_sx_offset(nph.mv.k) : (size_t)nbp * 40 + 256;
+                const unsigned sx = (unsigned)__cvta_generic_to_shared(work + xoff);      // = s_x of the phase's prologue
                 const float* xg = nph.x;
                 for (int i = threadIdx.x; i < (nph.mv.k >> 2); i += MK_THREADS)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx + i * 16), "l"(xg + i * 4) : "memory");
@@ -812,6 +950,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
 
 // working shared memory of one phase (the staging area of the norm weights comes on top, see cc_launch_mega)
 size_t cc_mega_smem_for_phase(const MkPhase& ph) {
+    if (ph.type == MK_MATVEC && ph.act_type == CC_Q8_K) return (size_t)(((TKBase::smem_bytes(ph.mv.k) + 15) & ~15) + 256) + (size_t)ph.mv.k * 4;
     if (ph.type == MK_MATVEC) {
         const size_t k = (size_t)ph.mv.k, nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
         // quants | scales | block sums | prologue: reduction scratch, f32 x
@@ -836,7 +975,7 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
     for (int rep = 0; rep < 4; rep++) {
         CC_CUDA(dev, cudaMemsetAsync(d_bar, 0, 4096, dev->stream));
         cudaEventRecord(e0, dev->stream);
-        int rc = cc_launch_mega(dev, d_tab, n, nullptr, d_bar, 1024, 0, nullptr, nullptr);
+        int rc = cc_launch_mega(dev, d_tab, n, nullptr, d_bar, 1024, 0, nullptr, nullptr, false);
         if (rc) return rc;
         cudaEventRecord(e1, dev->stream);
         CC_CUDA(dev, cudaEventSynchronize(e1));
@@ -848,6 +987,10 @@ extern "C" CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* u
     return CC_OK;
 }
 
+bool cc_mega_generic_supported(int type, int64_t k) {
+    return (type == CC_Q2_K || type == CC_Q3_K || type == CC_Q4_K || type == CC_Q5_K || type == CC_Q6_K || type == CC_Q8_K) && k % 256 == 0 && k <= 32768;
+}
+
 // developer A/B switches: CRABML_MEGA_FLAGS replaces the default flag word (see MK_F_* and the L2 budget byte)
 #define MK_DEFAULT_FLAGS (MK_F_LOOK | MK_F_WSTAGE | MK_F_POLLCNT | MK_F_XEARLY)      // profiles/r02c: 2407 us vs 2586 us (0x5) on the same box
 int cc_mega_flags() {
@@ -856,14 +999,15 @@ int cc_mega_flags() {
 }
 
 int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem_work, size_t smem_wstage,
-                   unsigned long long* prof, const CommDev* comm) {
+                   unsigned long long* prof, const CommDev* comm, bool generic) {
     const int flags = cc_mega_flags();
     int max_ctas_per_sm = 0;
     const size_t wtop = (smem_work + 15) & ~(size_t)15;
     const size_t smem = wtop + smem_wstage;
     CC_REQUIRE(dev, smem <= 227 * 1024, "megakernel: a phase needs %zu bytes of shared memory", smem);
-    if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, mega_kernel, MK_THREADS, smem));
+    auto kern = generic ? mega_kernel<true> : mega_kernel<false>;
+    if (smem > 48 * 1024) CC_CUDA(dev, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CC_CUDA(dev, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas_per_sm, kern, MK_THREADS, smem));
     CC_REQUIRE(dev, max_ctas_per_sm >= 1, "megakernel does not fit on an SM");
     int per_sm = max_ctas_per_sm < MK_CTAS_PER_SM ? max_ctas_per_sm : MK_CTAS_PER_SM;
     int grid = dev->sm_count * per_sm;          // all CTAs co-resident: required by the grid barrier
@@ -883,7 +1027,7 @@ int cc_launch_mega(cc_device* dev, const MkPhase* phases_dev, int n_phases, cons
     attr[0].val.cooperative = getenv("CRABML_MEGA_COOP") ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const uint16_t* lut = dev->exp_lut;
-    CC_CUDA(dev, cudaLaunchKernelEx(&cfg, mega_kernel, phases_dev, n_phases, dyn_dev, bar_dev, lut, prof, flags, (int)wtop, dev->err_host, (const CommDev)cd));
+    CC_CUDA(dev, cudaLaunchKernelEx(&cfg, kern, phases_dev, n_phases, dyn_dev, bar_dev, lut, prof, flags, (int)wtop, dev->err_host, (const CommDev)cd));
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }

@@ -191,3 +191,36 @@ int cc_launch_batch_matmul(cc_device* dev, const float* a, const void* b, int b_
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }
+
+// ---- greedy sampling on the device: sampler.rs:109-116 (`max_by` keeps the LAST maximum; NaN never wins) -------------------------
+// one CTA; thread t scans t, t + 512, ...; ties resolve to the larger index at every level, so the result is the last maximum
+__device__ __forceinline__ void argmax_merge(float& bv, long long& bi, float ov, long long oi) {
+    if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; }
+}
+__global__ void __launch_bounds__(CC_RED_THREADS) argmax_kernel(const float* __restrict__ x, long long n, long long* slot, long long* hist,
+                                                               const long long* hist_index_dev, long long hist_index) {
+    __shared__ float sv[CC_RED_WARPS];
+    __shared__ long long si[CC_RED_WARPS];
+    float bv = 0.0f; long long bi = -1;
+    for (long long i = threadIdx.x; i < n; i += CC_RED_THREADS) { const float v = x[i]; if (bi < 0 || !(v < bv)) { bv = v; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        argmax_merge(bv, bi, ov, oi);
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < CC_RED_WARPS; w++) argmax_merge(bv, bi, sv[w], si[w]);
+        if (bi < 0) bi = 0;
+        *slot = bi;
+        const long long h = hist_index_dev ? *hist_index_dev : hist_index;
+        if (hist && h >= 0 && h < CC_HISTORY_CAP) hist[h] = bi;
+    }
+}
+int cc_launch_argmax(cc_device* dev, const float* x, int64_t n, int64_t* slot, int64_t* hist, const int64_t* hist_index_dev, int64_t hist_index) {
+    argmax_kernel<<<1, CC_RED_THREADS, 0, dev->stream>>>(x, (long long)n, (long long*)slot, (long long*)hist, (const long long*)hist_index_dev, (long long)hist_index);
+    CC_LAUNCH_CHECK(dev);
+    return CC_OK;
+}

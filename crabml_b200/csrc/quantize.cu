@@ -4,6 +4,7 @@
 //   Q8_K: buf_q8_k.rs:84-131   scale = -128/max_signed, q = min(round_half_away(scale*x),127), d = 1/scale
 // Compiled with -fmad=false and IEEE division: results are bit-identical to the reference.
 #include "common.cuh"
+#include "quantize_dev.cuh"
 
 static size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -73,7 +74,7 @@ __global__ void quantize_q8_1_kernel(const float* __restrict__ x, int64_t nblock
     if (lane == 0) a.ds[b] = __halves2half2(__float2half_rn(d), __float2half_rn((float)s * d));
 }
 
-// one warp per 256-element super-block; lane handles elements lane*8 .. lane*8+7
+// one warp per 256-element super-block; lane handles elements lane*8 .. lane*8+7 (cc_quant_q8k_sblock, quantize_dev.cuh)
 __global__ void quantize_q8_k_kernel(const float* __restrict__ x, int64_t nsb, ActQ8_K a) {
     int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -82,43 +83,7 @@ __global__ void quantize_q8_k_kernel(const float* __restrict__ x, int64_t nsb, A
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = xb[i];
-    // first occurrence of the maximum |x| (strict `>` in buf_q8_k.rs:92-98)
-    float best_abs = 0.0f, best_val = 0.0f;
-    int best_idx = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float av = fabsf(v[i]);
-        if (av > best_abs) { best_abs = av; best_val = v[i]; best_idx = lane * 8 + i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float oa = __shfl_xor_sync(0xffffffffu, best_abs, o);
-        float ov = __shfl_xor_sync(0xffffffffu, best_val, o);
-        int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-        if (oa > best_abs || (oa == best_abs && oi < best_idx)) { best_abs = oa; best_val = ov; best_idx = oi; }
-    }
-    int8_t q[8];
-    int s0 = 0;
-    float d = 0.0f;
-    if (best_abs == 0.0f) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) q[i] = 0;
-    } else {
-        float scale = -128.0f / best_val;
-        d = 1.0f / scale;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            float r = fminf(roundf(scale * v[i]), 127.0f);      // f32::round = half away from zero (B3)
-            int qi = __float2int_rz(r);
-            qi = max(qi, -128);
-            q[i] = (int8_t)qi;
-            s0 += qi;
-        }
-    }
-    *reinterpret_cast<int2*>(a.qs + b * 256 + lane * 8) = *reinterpret_cast<int2*>(q);
-    int s1 = __shfl_down_sync(0xffffffffu, s0, 1);
-    if ((lane & 1) == 0) a.bsums[b * 16 + (lane >> 1)] = (int16_t)(s0 + s1);
-    if (lane == 0) a.d[b] = d;
+    cc_quant_q8k_sblock(v, lane, a.qs + b * 256, a.d + b, a.bsums + b * 16);
 }
 
 __global__ void quantize_f16_kernel(const float* __restrict__ x, int64_t n, __half* out) {   // buf/api.rs:198

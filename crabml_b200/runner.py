@@ -92,6 +92,18 @@ class LlamaRunner:
         self._check(self.device.lib.ccr_runner_generate_greedy(self.handle, p, len(prompt), steps, eos, out, C.byref(n)))
         return [int(out[i]) for i in range(n.value)]
 
+    def generate_greedy_logits(self, prompt, steps):
+        """ccr_runner_generate_greedy_ex with eos < 0: every step is submitted without waiting for the host (sampling on the device, the
+        sampled id feeds the next step from a device slot); returns (ids, logits[steps, vocab]) -- the logits of every generated
+        position are exported asynchronously through a pinned staging ring."""
+        p = (C.c_int64 * len(prompt))(*[int(t) for t in prompt])
+        out = (C.c_int64 * max(1, steps))()
+        n = C.c_int32(0)
+        logits = np.zeros((max(1, steps), self.conf.vocab_size), np.float32)
+        self._check(self.device.lib.ccr_runner_generate_greedy_ex(self.handle, p, len(prompt), steps, -1, out, C.byref(n),
+                                                                  logits.ctypes.data_as(C.c_void_p)))
+        return [int(out[i]) for i in range(n.value)], logits[:n.value]
+
     def close(self):
         if self.handle:
             self.device.lib.ccr_runner_destroy(self.handle)

@@ -141,6 +141,20 @@ CC_API int cc_debug_tensor_tap(cc_device* dev, const char* name, const cc_view* 
 /* returns element count via *n; copies min(*n_in, count) floats when dst != NULL */
 CC_API int cc_dump_debug_tensor(cc_device* dev, const char* name, float* dst, size_t* n);
 
+/* ---- greedy decoding without a host round trip per token (extension; not part of the reference's trait) ----------------
+ * The sampled token id stays on the device: cc_argmax_to_slot (sampler.rs:109-116, the LAST maximum) writes it to one of 16 slots
+ * and, when hist_index >= 0, to a device-side history; cc_copy_rows_from_slot is copy_rows_from with the single row index taken
+ * from a slot (the next token's embedding lookup).  The host can therefore submit token t+1 before token t has finished;
+ * cc_read_history synchronises and returns the ids.  cc_tensor_export_f32_async enqueues an export without waiting (dst should
+ * be pinned: cc_host_alloc) -- it is complete after the next synchronising call. */
+CC_API int cc_argmax_to_slot(cc_device* dev, const cc_view* x, int32_t slot, int64_t hist_index);
+CC_API int cc_copy_rows_from_slot(cc_device* dev, const cc_view* dst, const cc_view* src, int32_t slot);
+CC_API int cc_slot_set(cc_device* dev, int32_t slot, int64_t value);
+CC_API int cc_read_history(cc_device* dev, int64_t first, int64_t count, int64_t* out);
+CC_API int cc_tensor_export_f32_async(cc_device* dev, const cc_view* src, float* dst, size_t n);
+CC_API int cc_host_alloc(cc_device* dev, size_t bytes, void** out);
+CC_API void cc_host_free(cc_device* dev, void* p);
+
 /* ---- test / bench hooks (not part of the trait) ---------------------------------------------- */
 /* quantize an F32 vector exactly as matmul_vec does internally and return the reference-layout
  * activation blocks (Q8_0 / Q8_1 / Q8_K bytes) to the host: parity tests of a3-a5. */

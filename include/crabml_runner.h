@@ -52,6 +52,12 @@ CC_API int64_t ccr_runner_kv_cache_len(ccr_runner* r);                /* llama2.
 CC_API int ccr_runner_generate_greedy(ccr_runner* r, const int64_t* prompt, int32_t n_prompt, int32_t steps,
                                       int64_t eos_token, int64_t* out_tokens, int32_t* n_out);
 
+/* the same loop with the logits of every generated position exported asynchronously (logits_out: steps x vocab floats, may be
+ * NULL).  Sampling runs on the device (cc_argmax_to_slot) and the sampled id feeds the next step from a device slot: with
+ * eos_token < 0 no step waits for the host. */
+CC_API int ccr_runner_generate_greedy_ex(ccr_runner* r, const int64_t* prompt, int32_t n_prompt, int32_t steps,
+                                         int64_t eos_token, int64_t* out_tokens, int32_t* n_out, float* logits_out);
+
 #ifdef __cplusplus
 }
 #endif

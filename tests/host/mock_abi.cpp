@@ -4,6 +4,7 @@
 // the trace with the one the Python replay of the reference's forward() (oracle/llama_replay.py, which reproduces the
 // reference's golden generations on the CPU oracle) produces on a trace-only tensor class.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -103,4 +104,26 @@ CC_API int cc_batch_matmul(cc_device*, const cc_view* a, const cc_view* b, cc_bu
 CC_API int cc_debug_tensor_tap(cc_device*, const char* name, const cc_view*) { g_trace.push_back(std::string("tap ") + name); return CC_OK; }
 CC_API int cc_all_reduce_sum_inplace(cc_device*, const cc_view* x) { g_trace.push_back("all_reduce " + V(x)); return CC_OK; }
 CC_API int cc_all_gather(cc_device*, const cc_view* dst, const cc_view* src) { g_trace.push_back("all_gather dst=" + V(dst) + " src=" + V(src)); return CC_OK; }
+// greedy decoding on the device (ccr_runner_generate_greedy): the mock's "device" always samples token 7
+CC_API int cc_copy_rows_from_slot(cc_device*, const cc_view* dst, const cc_view* src, int32_t slot) {
+    g_trace.push_back("copy_rows_from_slot dst=" + V(dst) + " src=" + V(src) + " slot=" + std::to_string(slot));
+    return CC_OK;
+}
+CC_API int cc_argmax_to_slot(cc_device*, const cc_view* x, int32_t slot, int64_t hist) {
+    g_trace.push_back("argmax_to_slot " + V(x) + " slot=" + std::to_string(slot) + " hist=" + std::to_string((long long)hist));
+    return CC_OK;
+}
+CC_API int cc_read_history(cc_device*, int64_t first, int64_t count, int64_t* out) {
+    g_trace.push_back("read_history first=" + std::to_string((long long)first) + " count=" + std::to_string((long long)count));
+    for (int64_t i = 0; i < count; i++) out[i] = 7;
+    return CC_OK;
+}
+CC_API int cc_tensor_export_f32_async(cc_device*, const cc_view* src, float* dst, size_t n) {
+    g_trace.push_back("export_async " + V(src) + " n=" + std::to_string(n));
+    for (size_t i = 0; i < n; i++) dst[i] = 0.0f;
+    return CC_OK;
+}
+CC_API int cc_device_synchronize(cc_device*) { g_trace.push_back("synchronize"); return CC_OK; }
+CC_API int cc_host_alloc(cc_device*, size_t bytes, void** out) { *out = malloc(bytes ? bytes : 1); return CC_OK; }
+CC_API void cc_host_free(cc_device*, void* p) { free(p); }
 }

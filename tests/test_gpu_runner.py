@@ -197,3 +197,37 @@ def test_execution_modes_bit_identical_on_fixture(fixture_path, fname, f16_kv):
             dev.close()
     for mode in (1, 2):
         np.testing.assert_array_equal(res[mode].view(np.uint32), res[0].view(np.uint32), err_msg=f"lazy={mode} vs eager")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_device_side_greedy_loop_equals_the_host_sampled_loop(fixture_path, mode):
+    """ccr_runner_generate_greedy_ex (sampling on the device, the id feeds the next step from a device slot, no host wait per step)
+    against the plain loop forward -> export -> host argmax (sampler.rs:109-116): same ids, and the asynchronously exported logits of
+    every generated position are bit-identical to the synchronously exported ones."""
+    from crabml_b200 import runner as R
+    path = fixture_path("tinyllamas-stories-15m-q8_0.gguf")
+    dev = make_device(lazy=mode)
+    try:
+        conf, w, tok = R.load_gguf(path, dev)
+        steps = 12
+        r = R.LlamaRunner(dev, conf, w, 64)
+        ids, logits = r.generate_greedy_logits(PROMPT_IDS, steps)
+        assert len(ids) == steps and logits.shape == (steps, conf.vocab_size)
+        assert r.kv_cache_len() == len(PROMPT_IDS) + steps - 1
+        r.close()
+        r2 = R.LlamaRunner(dev, conf, w, 64)
+        pos, want_ids, want_logits = 0, [], []
+        for t in PROMPT_IDS:
+            lg = r2.forward([t], pos).copy(); pos += 1
+        for _ in range(steps):
+            nxt = int(np.flatnonzero(lg == lg.max())[-1])
+            want_ids.append(nxt); want_logits.append(lg)
+            if len(want_ids) == steps:
+                break
+            lg = r2.forward([nxt], pos).copy(); pos += 1
+        r2.close()
+        assert ids == want_ids
+        np.testing.assert_array_equal(logits.view(np.uint32), np.stack(want_logits).view(np.uint32))
+        assert ids[:11] == CASES[0][2]                      # and they are the reference's golden generation
+    finally:
+        dev.close()

@@ -191,3 +191,50 @@ def test_cpp_runner_issues_the_reference_op_sequence(mock_runner, name, conf, f1
         assert sum(1 for ln in got if ln.startswith("all_reduce")) == len(steps) * 2 * conf.n_layers
         assert sum(1 for ln in got if ln.startswith("all_gather")) == len(steps)
     assert per_token > 0
+
+
+def test_cpp_runner_greedy_loop_keeps_the_reference_forward_and_samples_on_the_device(mock_runner):
+    """ccr_runner_generate_greedy: the op sequence of every step is the reference's forward() (llama2.rs:184-281) with two
+    substitutions only -- the embedding lookup of a generated token reads its id from a device slot, and the sampler's argmax
+    (sampler.rs:109-116) runs on the device -- and the step budget follows llama2.rs:141-152 (first token from the prompt pass,
+    then min(steps - 1, seq_len - pos - 1) more)."""
+    L = mock_runner
+    conf = OConf(6, 6, 2, 288, 768, 256, 32000, 1e-5, 48)
+    dim, nl = conf.embedding_dim, conf.n_layers
+    keep = []
+
+    def arr(dtype, n):
+        a = (C.c_void_p * nl)(*[L.mock_new_buf(dtype, n) for _ in range(nl)])
+        keep.append(a)
+        return C.cast(a, C.POINTER(C.c_void_p))
+    wt = oc.Q8_0
+    w = capi.ccr_llama_weights(L.mock_new_buf(wt, conf.vocab_size * dim), arr(wt, dim * dim), arr(wt, dim * dim), arr(wt, dim * dim), arr(wt, dim * dim),
+                               arr(wt, 768 * dim), arr(wt, dim * 768), arr(wt, 768 * dim), arr(oc.F32, dim), arr(oc.F32, dim), L.mock_new_buf(oc.F32, dim),
+                               L.mock_new_buf(wt, conf.vocab_size * dim))
+    cconf = capi.ccr_llama_config(6, 6, nl, dim, 768, 256, 32000, 48, 1e-5, 0, 0, 1, 768)
+    h = C.c_void_p()
+    assert L.ccr_runner_create(L.mock_device(), C.byref(cconf), C.byref(w), 32, C.byref(h)) == 0
+    L.ccr_runner_generate_greedy.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    L.mock_trace_clear()
+    prompt = (C.c_int64 * 2)(1, 365)
+    out = (C.c_int64 * 8)()
+    n = C.c_int32(0)
+    assert L.ccr_runner_generate_greedy(h, prompt, 2, 4, -1, out, C.byref(n)) == 0, L.ccr_runner_last_error(h)
+    buf = C.create_string_buffer(int(L.mock_trace_size()) + 1)
+    L.mock_trace_copy(buf)
+    got = buf.value.decode().splitlines()
+    L.ccr_runner_destroy(h)
+    assert n.value == 4 and list(out[:4]) == [7, 7, 7, 7]
+    # reference forwards of the same 5 positions: prompt[0], prompt[1], then three generated tokens
+    want = _py_trace(conf, wt, wt, False, None, [(0, 1), (1, 365), (2, 0), (3, 0), (4, 0)], 32)[2 * nl:]     # skip the KV-cache allocs
+    norm = []
+    for ln in got:
+        if ln.startswith("copy_rows_from_slot"):
+            ln = ln.replace("copy_rows_from_slot", "copy_rows_from").replace(" slot=0", " rows=[0]")
+        norm.append(ln)
+    body = [ln for ln in norm if not ln.startswith(("argmax_to_slot", "flush", "read_history", "export"))]
+    ref = [ln for ln in want if not ln.startswith("export")]
+    assert body == ref
+    assert [ln for ln in got if ln.startswith("argmax_to_slot")] == [f"argmax_to_slot [32000]/[1]:0 slot=0 hist={i}" for i in range(4)]
+    assert got[-1] == "read_history first=0 count=4"
+    assert sum(1 for ln in got if ln.startswith("copy_rows_from_slot")) == 3
