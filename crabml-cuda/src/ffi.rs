@@ -69,6 +69,7 @@ extern "C" {
         n_out: *mut c_int,
     ) -> c_int;
     pub fn cc_device_launch_count(dev: *mut cc_device) -> u64;
+    pub fn cc_device_set_sm_limit(dev: *mut cc_device, n: i32) -> c_int;
     pub fn cc_device_stream(dev: *mut cc_device) -> *mut c_void;
 
     // ---- storage: Tensor::from_cpu / alloc / Clone / Drop (api.rs:14-23) ----
@@ -145,6 +146,7 @@ extern "C" {
     // ---- sharded decode: the exchange step ----
     pub fn cc_comm_create(dev: *mut cc_device, rank: i32, world: i32, handle_out_64: *mut u8) -> c_int;
     pub fn cc_comm_connect(dev: *mut cc_device, handles_world_x_64: *const u8) -> c_int;
+    pub fn cc_comm_connect_local(dev: *mut cc_device, peers: *const *mut cc_device) -> c_int;
     pub fn cc_comm_nccl_unique_id(dev: *mut cc_device, id_out_128: *mut u8) -> c_int;
     pub fn cc_comm_init_nccl(dev: *mut cc_device, id_128: *const u8) -> c_int;
     pub fn cc_comm_rank(dev: *mut cc_device) -> i32;

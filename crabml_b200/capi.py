@@ -119,6 +119,8 @@ def load_library(build_if_missing: bool = True):
         "cc_comm_create": (i32, [vp, i32, i32, vp]),
         "cc_comm_connect": (i32, [vp, vp]),
         "cc_comm_nccl_unique_id": (i32, [vp, vp]),
+        "cc_comm_connect_local": (i32, [vp, vp]),
+        "cc_device_set_sm_limit": (i32, [vp, i32]),
         "cc_comm_init_nccl": (i32, [vp, vp]),
         "cc_comm_rank": (i32, [vp]),
         "cc_comm_world_size": (i32, [vp]),

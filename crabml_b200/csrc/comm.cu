@@ -64,6 +64,7 @@ struct cc_comm {
     uint8_t* local = nullptr;
     uint8_t* peer[CC_COMM_MAX_RANKS] = {nullptr};
     bool connected = false;
+    bool local_peers = false;      // peers are devices of this process (cc_comm_connect_local): nothing to unmap
     ncclComm_t nccl = nullptr;
     CommDev cd = {};
 };
@@ -122,6 +123,29 @@ extern "C" CC_API int cc_comm_nccl_unique_id(cc_device* dev, uint8_t* id_out /* 
     return CC_OK;
 }
 
+// The same wiring for ranks that live in ONE process (one cc_device per rank; on different GPUs with peer access, or on the same
+// GPU for the single-GPU world-of-2 test): the peers' windows are ordinary device pointers, no IPC handle is needed.
+extern "C" CC_API int cc_comm_connect_local(cc_device* dev, cc_device* const* peers) {
+    if (!dev || !dev->comm || !peers) return cc_fail(dev, CC_ERR_ARG, "cc_comm_connect_local: create the communicator first");
+    CC_ENTER(dev);
+    cc_comm* c = dev->comm;
+    for (int p = 0; p < c->world; p++) {
+        CC_REQUIRE(dev, peers[p] && peers[p]->comm && peers[p]->comm->world == c->world && peers[p]->comm->rank == p, "cc_comm_connect_local: peer %d has no matching communicator", p);
+        if (peers[p]->ordinal != dev->ordinal) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(peers[p]->ordinal, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cc_fail(dev, CC_ERR_CUDA, "peer access to device %d: %s", peers[p]->ordinal, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        c->peer[p] = peers[p]->comm->local;
+    }
+    c->cd.rank = c->rank; c->cd.world = c->world;
+    for (int p = 0; p < c->world; p++) { c->cd.flag[p] = (unsigned*)c->peer[p]; c->cd.data[p] = (float*)(c->peer[p] + COMM_DATA_OFF); }
+    c->cd.seq = (unsigned*)(c->local + 4096);
+    c->connected = true;
+    c->local_peers = true;
+    return CC_OK;
+}
+
 // NCCL baseline transport: every rank passes rank 0's unique id (collective call).
 extern "C" CC_API int cc_comm_init_nccl(cc_device* dev, const uint8_t* id) {
     if (!dev || !dev->comm || !id) return cc_fail(dev, CC_ERR_ARG, "cc_comm_init_nccl: create the communicator first");
@@ -138,7 +162,7 @@ void cc_comm_destroy(cc_device* dev) {
     cc_comm* c = dev->comm;
     if (!c) return;
     if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
-    for (int p = 0; p < c->world; p++) if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+    if (!c->local_peers) for (int p = 0; p < c->world; p++) if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
     if (c->local) cudaFree(c->local);
     delete c;
     dev->comm = nullptr;
@@ -150,8 +174,10 @@ extern "C" CC_API int32_t cc_comm_world_size(cc_device* dev) { return dev && dev
 // mode 0: x[i] = sum_p part_p[i] (+ residual[i])      (n elements, in place)
 // mode 1: dst[p * n + i] = src_p[i]                   (allgather of n-element slices)
 #define XC_THREADS 1024
-__global__ void __launch_bounds__(XC_THREADS) exchange_kernel(CommDev c, float* x, const float* residual, float* dst, int n, int mode) {
+__global__ void __launch_bounds__(XC_THREADS) exchange_kernel(CommDev c, float* x, const float* residual, float* dst, int n, int mode, unsigned* err_dev, unsigned* err_host) {
     __shared__ unsigned s_seq;
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = 0;
     if (threadIdx.x == 0) s_seq = *c.seq + 1u;
     __syncthreads();
     const unsigned seq = s_seq;
@@ -167,9 +193,11 @@ __global__ void __launch_bounds__(XC_THREADS) exchange_kernel(CommDev c, float* 
     if (threadIdx.x < c.world) {
         cc_st_release_sys(c.flag[threadIdx.x] + c.rank * 32, seq);
         const unsigned* mine = c.flag[c.rank] + threadIdx.x * 32;
-        while ((int)(cc_ld_acquire_sys(mine) - seq) < 0) { }
+        CcSpin sp;
+        while ((int)(cc_ld_acquire_sys(mine) - seq) < 0) if (sp.expired(err_dev, err_host, 3u)) { s_abort = 1; break; }      // a peer never arrived
     }
     __syncthreads();
+    if (s_abort) return;
     const float* base = c.data[c.rank] + slot * CC_COMM_MAX_ELEMS;
     if (mode == 0) {
         for (int i = threadIdx.x; i < n4; i += XC_THREADS) {
@@ -206,7 +234,7 @@ int cc_launch_all_reduce(cc_device* dev, float* x, int64_t n, const float* resid
         return CC_OK;
     }
     CC_REQUIRE(dev, c->connected, "all_reduce: communicator not connected");
-    exchange_kernel<<<1, XC_THREADS, 0, dev->stream>>>(c->cd, x, residual, nullptr, (int)n, 0);
+    exchange_kernel<<<1, XC_THREADS, 0, dev->stream>>>(c->cd, x, residual, nullptr, (int)n, 0, dev->err_dev, dev->err_host);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }
@@ -222,7 +250,7 @@ int cc_launch_all_gather(cc_device* dev, const float* src, int64_t n, float* dst
         return CC_OK;
     }
     CC_REQUIRE(dev, c->connected, "all_gather: communicator not connected");
-    exchange_kernel<<<1, XC_THREADS, 0, dev->stream>>>(c->cd, (float*)src, nullptr, dst, (int)n, 1);
+    exchange_kernel<<<1, XC_THREADS, 0, dev->stream>>>(c->cd, (float*)src, nullptr, dst, (int)n, 1, dev->err_dev, dev->err_host);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }

@@ -55,6 +55,7 @@ struct cc_buf {
     int64_t rows = 0, cols = 0;  // quantized matrices
     uint8_t* plane[CC_MAX_PLANES] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t* raw = nullptr;    // GGUF-layout copy, kept only on exact_order devices (exact.cu)
+    void* f16 = nullptr;       // dequantised f16 [rows][cols] tile source of the prefill GEMM, built at first use (prefill_gemm.cu)
 };
 
 // On-device activation formats: what buf/api.rs:195-228 `quantize` produces, as SoA.
@@ -122,7 +123,13 @@ struct cc_device {
     // of sampled ids, both in device memory
     int64_t* slots = nullptr;         // [CC_N_SLOTS]
     int64_t* history = nullptr;       // [CC_HISTORY_CAP]
-    unsigned* err_host = nullptr;     // host-mapped word a persistent kernel raises when one of its bounded spins times out (mega.cu)
+    unsigned* err_host = nullptr;     // host-mapped word a kernel raises when one of its bounded spins times out (mega.cu, comm.cu)
+    unsigned* err_dev = nullptr;      // device copy polled by the other spinners of the same GPU
+
+    // weight upload (Tensor::from_cpu): double-buffered pinned staging so that reading the caller's bytes (page-faulting a GGUF mmap)
+    // overlaps the DMA of the previous chunk and the repack kernels of the previous tensor
+    void* up_pinned[2] = {nullptr, nullptr};
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
 
     // debug tap
     std::map<std::string, std::vector<float>> debug_tensors;
@@ -361,6 +368,30 @@ __device__ __forceinline__ unsigned cc_ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// ---- bounded spins: no wait in this library can hang the GPU -----------------------------------------------------------------
+// After CC_SPIN_TIMEOUT_NS without progress (a CTA that never became resident because another tenant holds an SM, a peer GPU that
+// died) the waiter raises the error words -- the device copy for the other spinners, the host-mapped copy for
+// cc_check_async_error, which reports CC_ERR_CUDA "... timeout" at the next synchronising call -- and the kernel drains.
+#define CC_SPIN_CHECK 0x7FFFu                // iterations between two looks at the clock / the error word
+#define CC_SPIN_TIMEOUT_NS 4000000000ull     // a healthy barrier or handshake takes microseconds
+__device__ __forceinline__ unsigned long long cc_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+struct CcSpin {
+    unsigned it = 0; unsigned long long t0 = 0;
+    __device__ __forceinline__ bool expired(unsigned* err_dev, unsigned* err_host, unsigned code) {
+        if ((++it & CC_SPIN_CHECK) != 0) return false;
+        if (err_dev && *(volatile unsigned*)err_dev) return true;
+        const unsigned long long t = cc_globaltimer_ns();
+        if (!t0) { t0 = t; return false; }
+        if (t - t0 < CC_SPIN_TIMEOUT_NS) return false;
+        if (err_dev) atomicExch(err_dev, code);
+        if (err_host) { *(volatile unsigned*)err_host = code; __threadfence_system(); }
+        return true;
+    }
+};
 __device__ __forceinline__ float h2f_bits(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 __device__ __forceinline__ uint16_t f2h_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
 #endif

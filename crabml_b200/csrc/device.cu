@@ -87,7 +87,18 @@ extern "C" CC_API int cc_device_create(const cc_device_options* opts, cc_device*
     for (uint32_t x = 0; x < 65536; x++) lut[x] = f2h_host(gelu_single(h2f_host((uint16_t)x)));
     CREATE_CUDA(cudaMalloc(&dev->gelu_lut, 65536 * 2));
     CREATE_CUDA(cudaMemcpy(dev->gelu_lut, lut.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaHostAlloc((void**)&dev->err_host, 64, cudaHostAllocMapped));
+    *dev->err_host = 0u;
+    CREATE_CUDA(cudaMalloc((void**)&dev->err_dev, 256));
+    CREATE_CUDA(cudaMemset(dev->err_dev, 0, 256));
 #undef CREATE_CUDA
+    // scratch buffers are sized once for every realistic row (k up to 1M elements): growing them later means cudaFree, which waits
+    // for EVERY kernel of the context -- with several devices of one process on one GPU (in-process ranks) a peer may be spinning
+    // on this rank's exchange at that moment
+    if (cc_ensure_act_scratch(dev, (size_t)4 << 20) != CC_OK || cc_ensure_pinned(dev, (size_t)64 << 10) != CC_OK || cc_ensure_dev_idx(dev, (size_t)64 << 10) != CC_OK) {
+        delete dev;
+        return CC_ERR_CUDA;
+    }
     if (dev->lazy && !dev->exact) {
         dev->lz = cc_lazy_create(dev);
         if (!dev->lz) { cc_fail(nullptr, CC_ERR_CUDA, "lazy mode: could not allocate the dynamic-argument buffers"); delete dev; return CC_ERR_CUDA; }
@@ -107,7 +118,9 @@ extern "C" CC_API void cc_device_destroy(cc_device* dev) {
         for (uintptr_t p : kv.second) cudaFree((void*)p);
     if (dev->act_scratch) cudaFree(dev->act_scratch);
     if (dev->pinned) cudaFreeHost(dev->pinned);
+    for (int i = 0; i < 2; i++) { if (dev->up_pinned[i]) cudaFreeHost(dev->up_pinned[i]); if (dev->up_ev[i]) cudaEventDestroy(dev->up_ev[i]); }
     if (dev->err_host) cudaFreeHost(dev->err_host);
+    if (dev->err_dev) cudaFree(dev->err_dev);
     if (dev->slots) cudaFree(dev->slots);
     if (dev->history) cudaFree(dev->history);
     if (dev->dev_idx) cudaFree(dev->dev_idx);
@@ -127,6 +140,18 @@ extern "C" CC_API int cc_device_synchronize(cc_device* dev) {
     if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
     CC_CUDA(dev, cudaStreamSynchronize(dev->stream));
     return cc_check_async_error(dev);
+}
+// test / co-tenancy hook: persistent kernels of this device use at most `n` SMs (their grid = n CTAs), so that two devices of one
+// process can run their megakernels side by side on ONE GPU (tests/test_gpu_sharded.py: world of 2 on a single GPU)
+extern "C" CC_API int cc_device_set_sm_limit(cc_device* dev, int32_t n) {
+    if (!dev) return CC_ERR_ARG;
+    CC_ENTER(dev);
+    cudaDeviceProp prop;
+    CC_CUDA(dev, cudaGetDeviceProperties(&prop, dev->ordinal));
+    CC_REQUIRE(dev, n >= 1 && n <= prop.multiProcessorCount, "sm_limit %d out of range (1..%d)", n, prop.multiProcessorCount);
+    if (dev->lz) { int rc = cc_lazy_flush(dev); if (rc) return rc; }
+    dev->sm_count = n;
+    return CC_OK;
 }
 extern "C" CC_API int cc_device_flush(cc_device* dev) {
     if (!dev) return CC_ERR_ARG;
@@ -240,6 +265,7 @@ extern "C" CC_API void cc_tensor_release(cc_buf* b) {
     if (b->pooled) cc_pool_free(b->dev, b->base, b->bytes);
     else if (b->base) cudaFree(b->base);
     if (b->raw) cudaFree(b->raw);
+    if (b->f16) cudaFree(b->f16);
     delete b;
 }
 extern "C" CC_API int32_t cc_tensor_dtype(const cc_buf* b) { return b ? b->dtype : -1; }
@@ -257,6 +283,31 @@ extern "C" CC_API int cc_tensor_alloc(cc_device* dev, const int64_t* shape, int3
     CC_REQUIRE(dev, t == CC_F32 || t == CC_F16, "only f32/f16 is supported");   // cpu_tensor.rs:139-141
     // F32 is zero-filled (vec![0.0; n]); F16 is uninitialised in the reference (buf_f16.rs:23-28), zeroed here
     return cc_new_activation(dev, prod(shape, ndim), t, true, out);
+}
+
+// Host bytes -> device through two pinned 16 MB staging buffers (model.rs:462-477 hands over slices of the GGUF mmap: pageable and
+// usually not yet resident).  While chunk i is DMA'd, the host copies (= page-faults) chunk i+1 into the other buffer; nothing here
+// waits for the GPU except the reuse of a staging buffer, so uploads of consecutive tensors and their repack kernels overlap.
+#define CC_UP_CHUNK ((size_t)16 << 20)
+static int cc_upload_staged(cc_device* dev, void* dst, const void* src, size_t n) {
+    if (n <= ((size_t)1 << 20)) {
+        CC_CUDA(dev, cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, dev->stream));     // small: the driver's own staging is fine
+        return CC_OK;
+    }
+    for (int i = 0; i < 2; i++)
+        if (!dev->up_pinned[i]) {
+            CC_CUDA(dev, cudaMallocHost(&dev->up_pinned[i], CC_UP_CHUNK));
+            CC_CUDA(dev, cudaEventCreateWithFlags(&dev->up_ev[i], cudaEventDisableTiming));
+        }
+    int i = 0;
+    for (size_t off = 0; off < n; off += CC_UP_CHUNK, i ^= 1) {
+        const size_t len = n - off < CC_UP_CHUNK ? n - off : CC_UP_CHUNK;
+        CC_CUDA(dev, cudaEventSynchronize(dev->up_ev[i]));                      // the copy that last read this buffer is done
+        memcpy(dev->up_pinned[i], (const uint8_t*)src + off, len);
+        CC_CUDA(dev, cudaMemcpyAsync((uint8_t*)dst + off, dev->up_pinned[i], len, cudaMemcpyHostToDevice, dev->stream));
+        CC_CUDA(dev, cudaEventRecord(dev->up_ev[i], dev->stream));
+    }
+    return CC_OK;
 }
 
 extern "C" CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size_t nbytes, const int64_t* shape,
@@ -277,9 +328,9 @@ extern "C" CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size
         cudaError_t e = cudaMalloc(&b->base, need ? need : 1);
         if (e != cudaSuccess) { delete b; return cc_fail(dev, CC_ERR_CUDA, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); }
         b->plane[0] = (uint8_t*)b->base;
-        e = cudaMemcpyAsync(b->base, bytes, need, cudaMemcpyHostToDevice, dev->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(dev->stream);
-        if (e != cudaSuccess) { cudaFree(b->base); delete b; return cc_fail(dev, CC_ERR_CUDA, "upload: %s", cudaGetErrorString(e)); }
+        int urc = cc_upload_staged(dev, b->base, bytes, need);
+        if (urc == CC_OK && need <= ((size_t)1 << 20)) { e = cudaStreamSynchronize(dev->stream); if (e != cudaSuccess) urc = cc_fail(dev, CC_ERR_CUDA, "upload: %s", cudaGetErrorString(e)); }
+        if (urc != CC_OK) { cudaFree(b->base); delete b; return urc; }      // (small copies read the caller's buffer asynchronously: wait; staged ones were copied out)
         *out = b;
         return CC_OK;
     }
@@ -288,7 +339,7 @@ extern "C" CC_API int cc_tensor_from_cpu(cc_device* dev, const void* bytes, size
     uint8_t* staging = nullptr;
     cudaError_t e = cudaMalloc(&b->base, b->bytes ? b->bytes : 1);
     if (e == cudaSuccess) e = cudaMalloc(&staging, need ? need : 1);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(staging, bytes, need, cudaMemcpyHostToDevice, dev->stream);
+    if (e == cudaSuccess && cc_upload_staged(dev, staging, bytes, need) != CC_OK) e = cudaErrorUnknown;
     if (e != cudaSuccess) {
         if (b->base) cudaFree(b->base);
         if (staging) cudaFree(staging);

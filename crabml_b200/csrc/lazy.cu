@@ -94,10 +94,6 @@ LazyState* cc_lazy_create(cc_device* dev) {
     if (cudaMalloc(&lz->dyn_dev, lz->dyn_cap) != cudaSuccess) { delete lz; return nullptr; }
     if (getenv("CRABML_MEGA_PROF")) cudaMalloc(&lz->prof_dev, 8 * 8 * 4097);
     if (cudaMalloc(&lz->bar_dev, 4096) != cudaSuccess || cudaMemset(lz->bar_dev, 0, 4096) != cudaSuccess) { delete lz; return nullptr; }
-    if (!dev->err_host) {
-        if (cudaHostAlloc((void**)&dev->err_host, 64, cudaHostAllocMapped) != cudaSuccess) { delete lz; return nullptr; }
-        *dev->err_host = 0u;
-    }
     return lz;
 }
 void cc_lazy_destroy(cc_device* dev) {
@@ -358,6 +354,7 @@ struct Fuser {
             else P.steps.push_back([=](uint8_t*) { return cc_launch_all_gather(d, part, mrows, xdst); });
             MkPhase ph = {}; ph.type = xchg == 1 ? MK_REDUCE : MK_GATHER; ph.red_n = (int)mrows; ph.red_dst = xdst; ph.red_res = xres; P.phases.push_back(ph);
             if (!cc_comm_dev(dev) || cc_comm_is_nccl(dev)) P.mega_ok = false;      // NCCL baseline: graph of kernels + NCCL nodes (lazy mode 1)
+            if ((((mrows + dev->sm_count - 1) / dev->sm_count + 3) & ~(int64_t)3) > 512) P.mega_ok = false;   // one CTA's row block must fit the exchange stage (mega.cu MK_XSTAGE_ROWS)
         }
         for (size_t t = i; t < i + used; t++) q[t].done = true;
         return used;
@@ -597,7 +594,7 @@ int cc_lazy_flush(cc_device* dev) {
         cudaStreamSynchronize(dev->stream);
         graph_cache_clear(lz);                       // cached graphs hold the old scratch pointers
         for (int i = 0; i < 2; i++) { if (lz->act[i]) cudaFree(lz->act[i]); lz->act[i] = nullptr; }
-        size_t cap = 4096; while (cap < need) cap <<= 1;
+        size_t cap = (size_t)1 << 20; while (cap < need) cap <<= 1;      // generous from the start: growing means cudaFree (context-wide wait)
         for (int i = 0; i < 2; i++) if (cudaMalloc(&lz->act[i], cap) != cudaSuccess) return cc_fail(dev, CC_ERR_CUDA, "lazy: scratch alloc failed");
         lz->act_cap = cap;
     }
@@ -724,9 +721,10 @@ int cc_check_async_error(cc_device* dev) {
     const unsigned code = *(volatile unsigned*)dev->err_host;
     if (!code) return CC_OK;
     *(volatile unsigned*)dev->err_host = 0u;
+    if (dev->err_dev) cudaMemset(dev->err_dev, 0, 256);
     if (dev->lz && dev->lz->bar_dev) cudaMemset(dev->lz->bar_dev, 0, 4096);
-    return cc_fail(dev, CC_ERR_CUDA, "megakernel barrier timeout (%s): the grid was not co-resident or a peer GPU stopped responding",
-                   code == 2u ? "cross-GPU handshake" : "grid barrier");
+    return cc_fail(dev, CC_ERR_CUDA, "%s timeout (%s): the grid was not co-resident or a peer GPU stopped responding",
+                   code == 3u ? "exchange kernel" : "megakernel barrier", code == 1u ? "grid barrier" : "cross-GPU handshake");
 }
 
 // developer profiling: per-phase start timestamps (ns) of the last megakernel run + phase type codes

@@ -26,6 +26,7 @@
 #define MK_WARPS 16
 #define MK_CTAS_PER_SM 1
 #define MK_SEG 4
+#define MK_XSTAGE_ROWS 512         // exchange phases: rows of one CTA's contiguous block (2 KB stage in shared memory)
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -47,28 +48,11 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm vo
 __device__ __forceinline__ void red_add_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 #define MK_BAR_THREAD (MK_THREADS - 1)
 #define MK_BAR_ERR 64                        // bar[64]: non-zero once any spin on this GPU has timed out
-#define MK_SPIN_CHECK 0x7FFFu                // iterations between two looks at the clock / the error word
-#define MK_SPIN_TIMEOUT_NS 4000000000ull     // a healthy barrier takes microseconds
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-// Every spin is bounded: after MK_SPIN_TIMEOUT_NS without progress (a CTA that never became resident because another tenant holds
-// an SM, a peer GPU that died) the waiter raises the error word -- device copy for the other spinners, host-mapped copy for
-// cc_synchronize / cc_lazy_flush, which report CC_ERR_CUDA "megakernel barrier timeout" -- and the kernel drains.
+__device__ __forceinline__ unsigned long long globaltimer_ns() { return cc_globaltimer_ns(); }
+// every spin is bounded (CcSpin, common.cuh): a barrier that cannot complete ends in CC_ERR_CUDA "megakernel barrier timeout"
 struct MkSpin {
-    unsigned it = 0; unsigned long long t0 = 0;
-    __device__ __forceinline__ bool expired(unsigned* bar, unsigned* err_host, unsigned code) {
-        if ((++it & MK_SPIN_CHECK) != 0) return false;
-        if (*(volatile unsigned*)&bar[MK_BAR_ERR]) return true;
-        const unsigned long long t = globaltimer_ns();
-        if (!t0) { t0 = t; return false; }
-        if (t - t0 < MK_SPIN_TIMEOUT_NS) return false;
-        atomicExch(&bar[MK_BAR_ERR], code);
-        if (err_host) { *(volatile unsigned*)err_host = code; __threadfence_system(); }
-        return true;
-    }
+    CcSpin sp;
+    __device__ __forceinline__ bool expired(unsigned* bar, unsigned* err_host, unsigned code) { return sp.expired(&bar[MK_BAR_ERR], err_host, code); }
 };
 __device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen, bool xgpu = false) {
     __syncthreads();
@@ -232,7 +216,7 @@ struct MkPipe { MkSeg buf0, buf1; };      // register stages of the weight strea
 
 // geometry of one MATVEC phase for this warp
 struct MkGeo {
-    int nb, GR, NSEG, U, last_half_off, gw, TW;
+    int nb, GR, NSEG, U, last_half_off, gw, TW, rpc;
     bool pair;
 };
 __device__ __forceinline__ MkGeo mk_geo(const StreamArgs& A) {
@@ -245,7 +229,17 @@ __device__ __forceinline__ MkGeo mk_geo(const StreamArgs& A) {
     g.pair = A.epilogue == 2;
     const StreamMats& M = A.mats;
     const int m_cat = g.pair ? M.m[0] : M.m[0] + (M.n > 1 ? M.m[1] : 0) + (M.n > 2 ? M.m[2] : 0);
-    const int n_rows = g.gw < m_cat ? (m_cat - g.gw + g.TW - 1) / g.TW : 0;
+    int n_rows = g.gw < m_cat ? (m_cat - g.gw + g.TW - 1) / g.TW : 0;
+    g.rpc = 0;
+    if (A.epilogue == 3) {
+        // exchange phases: every CTA owns ONE contiguous block of rows (rpc rows, a multiple of 4), warp w takes the rows w, w + 16, ...
+        // of the block -- so the CTA's partial results are one contiguous run of floats and go to each peer as a single coalesced store
+        g.rpc = (((m_cat + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+        const int first = (int)blockIdx.x * g.rpc;
+        const int cnt = min(g.rpc, max(0, m_cat - first));
+        g.gw = first + warp; g.TW = MK_WARPS;
+        n_rows = warp < cnt ? (cnt - warp + MK_WARPS - 1) / MK_WARPS : 0;
+    }
     g.U = (g.pair ? 2 * n_rows : n_rows) * g.NSEG;
     g.last_half_off = 16 * (g.nb - 32 * (g.GR - 1));
     return g;
@@ -310,8 +304,8 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
         // (~2.1 us) plus its own latency chain.  The weight segments requested by matvec_prefetch are in flight meanwhile.
         const int n = k;
         const int warp = threadIdx.x >> 5;
-        float* s_red = (float*)(smem + (size_t)nbp * 40);                // scratch behind the activation arrays
-        float* s_x = s_red + 64;                                          // f32 copy of x
+        float* s_red = (float*)(smem + (size_t)nbp * 40);                // scratch behind the activation arrays (256 B), then the 2 KB exchange stage
+        float* s_x = s_red + 64 + 512;                                    // f32 copy of x
         {   // one L2 round trip: every 16-byte chunk of x (and of the norm weights) requested at once
             const int n4 = n >> 2;
             const unsigned sx = (unsigned)__cvta_generic_to_shared(s_x), sw = (unsigned)__cvta_generic_to_shared(s_w);
@@ -413,6 +407,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
     const int4* aq_l = (const int4*)s_q + 2 * lane;
     const float* ad_l = s_d + lane;
     const int* as_l = s_s + lane;
+    float* s_part = (float*)(smem + (size_t)nbp * 40 + 256);             // exchange stage: this CTA's block of partial rows (<= MK_XSTAGE_ROWS floats)
     float acc = 0.0f, first = 0.0f;
     int c_i = 0, c_seg = 0;
     // Epilogues that need a value from memory (the residual, or the exp LUT entry of silu) are finished ONE ROW LATER: the load
@@ -451,9 +446,8 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
         if (lane == 0) {
             int mat = 0, rr = gw + i * TW;
             if (M.n > 1 && rr >= M.m[0]) { rr -= M.m[0]; mat = 1; if (M.n > 2 && rr >= M.m[1]) { rr -= M.m[1]; mat = 2; } }
-            if (A.epilogue == 3) {         // partial row -> slot[rank] of every GPU's exchange window (NVLink peer stores)
-                const size_t off = ((size_t)((xseq + 1u) & 1u) * CC_COMM_MAX_RANKS + comm.rank) * CC_COMM_MAX_ELEMS + rr;
-                for (int pr = 0; pr < comm.world; pr++) comm.data[pr][off] = r;
+            if (A.epilogue == 3) {         // partial row -> this CTA's stage; sent to the peers as one run when the phase body is done
+                s_part[rr - (int)blockIdx.x * g.rpc] = r;
                 return;
             }
             float* o = mat == 0 ? M.out[0] : mat == 1 ? M.out[1] : M.out[2];
@@ -472,6 +466,19 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
         advance_load();
     }
     flush_pending();
+    if (A.epilogue == 3) {
+        // the CTA's block of partial rows -> slot[rank] of every GPU's exchange window: warp p serves peer p with ONE coalesced NVLink
+        // store of 16 bytes per lane (28 rows = 112 contiguous bytes at 7B shapes) instead of one 4-byte store per row and peer
+        __syncthreads();
+        const int warp = threadIdx.x >> 5;
+        const int first_row = (int)blockIdx.x * g.rpc;
+        const int m_all = M.m[0];
+        const int cnt = min(g.rpc, max(0, m_all - first_row));
+        if (warp < comm.world) {
+            const size_t off = ((size_t)((xseq + 1u) & 1u) * CC_COMM_MAX_RANKS + comm.rank) * CC_COMM_MAX_ELEMS + first_row;
+            for (int c4 = lane * 4; c4 < cnt; c4 += 128) *(float4*)(comm.data[warp] + off + c4) = *(const float4*)(s_part + c4);
+        }
+    }
     // this warp is done: its register stages are free, so it requests its first segments of the next MATVEC phase right away instead
     // of idling until the slowest warp of the CTA reaches the barrier (the tail of a phase becomes prefetch time)
     if (early_next) { if (early_next[0].wtype == CC_Q8_0) matvec_prefetch<CC_Q8_0>(early_next[0].mv, P); else if (early_next[0].wtype == CC_Q4_0) matvec_prefetch<CC_Q4_0>(early_next[0].mv, P); }
@@ -934,7 +941,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             const MkPhase& nph = s_phs[(p + 1) & 1];
             if ((flags & MK_F_XEARLY) && nph.type == MK_MATVEC && nph.x && !nph.red_n) {
                 const int nb = nph.mv.k >> 5, nbp = ((((nb + 31) >> 5) + MK_SEG - 1) / MK_SEG) * MK_SEG * 32;
-                const size_t xoff = nph.act_type == CC_Q8_K ? (size_t)mk_generic_sx_offset(nph.mv.k) : (size_t)nbp * 40 + 256;
+                const size_t xoff = nph.act_type == CC_Q8_K ? (size_t)mk_generic_sx_offset(nph.mv.k) : (size_t)nbp * 40 + 256 + 2048;
                 const unsigned sx = (unsigned)__cvta_generic_to_shared(work + xoff);      // = s_x of the phase's prologue
                 const float* xg = nph.x;
                 for (int i = threadIdx.x; i < (nph.mv.k >> 2); i += MK_THREADS)
@@ -954,7 +961,7 @@ size_t cc_mega_smem_for_phase(const MkPhase& ph) {
     if (ph.type == MK_MATVEC) {
         const size_t k = (size_t)ph.mv.k, nb = k / 32, GR = (nb + 31) / 32, NSEG = (GR + MK_SEG - 1) / MK_SEG, nbp = NSEG * MK_SEG * 32;
         // quants | scales | block sums | prologue: reduction scratch, f32 x
-        return nbp * 40 + 256 + (ph.x ? k * 4 : 0);
+        return nbp * 40 + 256 + 2048 + (ph.x ? k * 4 : 0);
     }
     if (ph.type == MK_ATTN) return (size_t)(3 * ph.at.hd + ((ph.at.max_len + 8 + 3) & ~3) + AT_NBUF * AT_CH * ph.at.hd) * 4 + 64;
     return 1024;

@@ -2,7 +2,8 @@
 // (Tensor::matmul_vec with a (b, k) rhs: cpu_tensor.rs:368-386, primitives/matmul_vec.rs:26-78; the prompt walk of
 // llama2.rs:111-139).  With b >= 32 rows the contraction is genuinely dense, so it runs on the 5th-generation tensor cores:
 //
-//   1. dequant_w_f16_kernel : GGUF quant blocks (device plane layout, any of the 11 weight types) -> f16 tile source [m][k]
+//   1. dequant_w_f16_kernel : GGUF quant blocks (device plane layout, any of the 11 weight types) -> f16 tile source [m][k], ONCE per
+//      weight (kept beside the quantised planes: 180 GB of HBM hold a 7B model's 14 GB of f16 many times over)
 //      (w = f32 dequantised value as BlockQ*::dequantize gives it, rounded once to f16: |q| <= 127 times an f16 scale)
 //   2. act_q8_to_f16_kernel : the activation is quantised to Q8_0 exactly like the decode path (buf_q8_0.rs:87-134) and the
 //      quantised value q * d is what enters the GEMM, so the only deviation from the reference is the f16 rounding of the two
@@ -271,20 +272,37 @@ static int pg_launch(cc_device* dev, const CUtensorMap& tw, const CUtensorMap& t
     return CC_OK;
 }
 
-// act: the quantisation of the (b, k) activation to the weight's partner type, Q8_0 or Q8_K (quantize.cu layout); out: f32 [b][m]
-int cc_launch_prefill_matmul(cc_device* dev, const cc_buf* w, const void* act_q8_0, float* out, int64_t m, int64_t k, int64_t b) {
-    PgScratch* s = pg_scratch(dev);
-    int rc = pg_ensure(dev, &s->w, &s->w_bytes, (size_t)m * k * 2);
-    if (rc) return rc;
-    rc = pg_ensure(dev, &s->x, &s->x_bytes, (size_t)b * k * 2);
-    if (rc) return rc;
+// Dequantised weights are kept: with 180 GB of HBM a 7B model's f16 tile source (2 bytes per weight, 13-14 GB) fits many times over,
+// and dequantising 58 MB per matrix on every call costs as much as the GEMM itself (profiles/r02e).  CRABML_PREFILL_NOCACHE=1 keeps
+// the round-trip through one reusable scratch buffer instead (memory-constrained deployments).
+static int pg_weight_f16(cc_device* dev, const cc_buf* w, int64_t m, int64_t k, PgScratch* s, const void** out) {
+    static const bool nocache = getenv("CRABML_PREFILL_NOCACHE") != nullptr;
+    cc_buf* wb = const_cast<cc_buf*>(w);
+    const bool cacheable = !nocache && m == w->rows && k == w->cols;
+    if (cacheable && wb->f16) { *out = wb->f16; return CC_OK; }
+    void* dst = nullptr;
+    if (cacheable) { CC_CUDA(dev, cudaMalloc(&dst, (size_t)m * k * 2)); }
+    else { int rc = pg_ensure(dev, &s->w, &s->w_bytes, (size_t)m * k * 2); if (rc) return rc; dst = s->w; }
     DeqPlanes pl;
     for (int i = 0; i < CC_MAX_PLANES; i++) pl.p[i] = w->plane[i];
     pl.cols = w->cols > 0 ? w->cols : k;
+    const int64_t n = m * k;
+    dequant_w_f16_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, dev->stream>>>(w->dtype, pl, n, (__half*)dst);
+    CC_LAUNCH_CHECK(dev);
+    if (cacheable) wb->f16 = dst;
+    *out = dst;
+    return CC_OK;
+}
+
+// act: the quantisation of the (b, k) activation to the weight's partner type, Q8_0 or Q8_K (quantize.cu layout); out: f32 [b][m]
+int cc_launch_prefill_matmul(cc_device* dev, const cc_buf* w, const void* act_q8_0, float* out, int64_t m, int64_t k, int64_t b) {
+    PgScratch* s = pg_scratch(dev);
+    const void* wf16 = nullptr;
+    int rc = pg_weight_f16(dev, w, m, k, s, &wf16);
+    if (rc) return rc;
+    rc = pg_ensure(dev, &s->x, &s->x_bytes, (size_t)b * k * 2);
+    if (rc) return rc;
     {
-        const int64_t n = m * k;
-        dequant_w_f16_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, dev->stream>>>(w->dtype, pl, n, (__half*)s->w);
-        CC_LAUNCH_CHECK(dev);
         const int64_t na = b * k;
         if (cc_partner_type(w->dtype) == CC_Q8_K) act_q8k_to_f16_kernel<<<(unsigned)((na / 2 + 255) / 256), 256, 0, dev->stream>>>(cc_act_q8_k((void*)act_q8_0, na), na, (__half*)s->x);
         else act_q8_to_f16_kernel<<<(unsigned)((na / 2 + 255) / 256), 256, 0, dev->stream>>>(cc_act_q8_0((void*)act_q8_0, na), na, (__half*)s->x);
@@ -292,7 +310,7 @@ int cc_launch_prefill_matmul(cc_device* dev, const cc_buf* w, const void* act_q8
     }
     const int block_n = b >= 192 ? 256 : b >= 96 ? 128 : 64;
     CUtensorMap tw, tx;
-    rc = pg_make_tmap(dev, &tw, s->w, m, k, PG_BLOCK_M);
+    rc = pg_make_tmap(dev, &tw, wf16, m, k, PG_BLOCK_M);
     if (rc) return rc;
     rc = pg_make_tmap(dev, &tx, s->x, b, k, block_n);
     if (rc) return rc;

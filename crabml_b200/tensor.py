@@ -109,6 +109,19 @@ class CudaTensorDevice:
             raise CudaError(f"unknown transport {transport}")
         self.rank, self.world = rank, world
 
+    def create_comm_local(self, rank, world):
+        """first half of an in-process world (every rank is a device of THIS process): allocate the exchange window"""
+        handle = (C.c_uint8 * 64)()
+        self.check(self.lib.cc_comm_create(self.handle, rank, world, handle))
+        self.rank, self.world = rank, world
+
+    def connect_comm_local(self, devices):
+        """second half: wire the windows of all ranks directly (devices[r] = the CudaTensorDevice of rank r)"""
+        arr = (C.c_void_p * len(devices))(*[d.handle.value if hasattr(d.handle, "value") else d.handle for d in devices])
+        self.check(self.lib.cc_comm_connect_local(self.handle, arr))
+
+    def set_sm_limit(self, n): self.check(self.lib.cc_device_set_sm_limit(self.handle, int(n)))
+
     def timer_begin(self): self.check(self.lib.cc_bench_timer_begin(self.handle))
 
     def timer_end(self) -> float:

@@ -94,6 +94,8 @@ CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase
 CC_API int cc_lazy_mega_profile(cc_device* dev, unsigned long long* ts, int* types, int cap, int* n_out);
 /* counters: kernels launched by this library since creation (bench.py "gpu_launches") */
 CC_API uint64_t cc_device_launch_count(cc_device* dev);
+/* persistent kernels of this device use at most n SMs (test / co-tenancy hook: two devices of one process side by side on one GPU) */
+CC_API int cc_device_set_sm_limit(cc_device* dev, int32_t n);
 /* raw cudaStream_t of the device, for event timing by the caller */
 CC_API void* cc_device_stream(cc_device* dev);
 
@@ -168,6 +170,8 @@ CC_API int cc_test_quantize_activation(cc_device* dev, const cc_view* x, int32_t
  * cc_comm_connect.  cc_comm_init_nccl switches the transport to NCCL (baseline; id from cc_comm_nccl_unique_id on rank 0). */
 CC_API int cc_comm_create(cc_device* dev, int32_t rank, int32_t world, uint8_t* handle_out_64);
 CC_API int cc_comm_connect(cc_device* dev, const uint8_t* handles_world_x_64);
+/* ranks that are devices of ONE process (peers[r] = the cc_device of rank r): windows are wired directly, no IPC handles */
+CC_API int cc_comm_connect_local(cc_device* dev, cc_device* const* peers);
 CC_API int cc_comm_nccl_unique_id(cc_device* dev, uint8_t* id_out_128);
 CC_API int cc_comm_init_nccl(cc_device* dev, const uint8_t* id_128);
 CC_API int32_t cc_comm_rank(cc_device* dev);

@@ -51,17 +51,23 @@ C2RUST = {"int": "c_int", "int32_t": "i32", "int64_t": "i64", "uint64_t": "u64",
 
 
 def _c_type_to_rust(t):
-    """'const cc_view*' -> '*const cc_view' ; 'cc_buf**' -> '*mut *mut cc_buf' ; 'int32_t' -> 'i32'"""
-    t = t.strip()
-    const = t.startswith("const ")
-    if const:
-        t = t[6:].strip()
-    stars = t.count("*")
-    base = t.replace("*", "").strip()
-    r = C2RUST[base]
-    for i in range(stars):
-        inner_const = const and i == 0
-        r = ("*const " if inner_const else "*mut ") + r
+    """'const cc_view*' -> '*const cc_view' ; 'cc_buf**' -> '*mut *mut cc_buf' ; 'cc_device* const*' -> '*const *mut cc_device'"""
+    toks = re.findall(r"\*|\w+", t)
+    const_next = False
+    words = []
+    while toks and toks[0] != "*":
+        w = toks.pop(0)
+        if w == "const":
+            const_next = True
+        else:
+            words.append(w)
+    r = C2RUST[" ".join(words)]
+    for tok in toks:
+        if tok == "*":
+            r = ("*const " if const_next else "*mut ") + r
+            const_next = False
+        elif tok == "const":
+            const_next = True
     return r
 
 
