@@ -482,12 +482,15 @@ def run_prefill(args, rank, world, local_rank):
         step()
     ms = dev.timer_end()
     launches = dev.launch_count() - l0
-    # e2e: the activations come from pinned host memory every step and the last-row logits go back
-    host_x = rng.standard_normal(b * dim).astype(np.float32)
+    # e2e: what crosses the host boundary in a prompt pass -- the token ids go host->device (the embedding rows are gathered on the
+    # device, llama2.rs:223-224), the logits of the last position come back
+    ids = [int(v) for v in rng.integers(0, conf.vocab_size, b)]
+    from crabml_b200 import capi as _capi
     dev.synchronize()
     dev.timer_begin(); t0 = time.perf_counter()
     for _ in range(K):
-        xd = CudaTensor.new(host_x, [b, dim], dev)
+        xd = CudaTensor.alloc([b, dim], _capi.F32, dev)
+        xd.copy_rows_from(weights["token_embed"], ids)
         for l in range(conf.n_layers):
             for key in ("wq", "wk", "wv", "wo", "ffn_gate", "ffn_up"):
                 weights[key][l].matmul_vec(xd)
@@ -506,7 +509,7 @@ def run_prefill(args, rank, world, local_rank):
                                 "batched forward are not part of this workload",
                        "l2_policy": f"{wbytes / 1e9:.2f} GB of weights and {b * hid * 4 / 1e6:.0f} MB activations per step: inputs larger than L2",
                        "flop_per_step": flops},
-            "e2e": {"value": b * K / (e2e_ms * 1e-3), "unit": "tok/s", "h2d_bytes_per_step": b * dim * 4, "d2h_bytes_per_step": conf.vocab_size * 4, "ms_per_step": e2e_ms / K},
+            "e2e": {"value": b * K / (e2e_ms * 1e-3), "unit": "tok/s", "h2d_bytes_per_step": b * 8, "d2h_bytes_per_step": conf.vocab_size * 4, "ms_per_step": e2e_ms / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "umma_gemm_kernel (prefill_gemm.cu): TMA -> smem ring -> tcgen05.mma kind::f16 -> TMEM -> tcgen05.ld epilogue",
                          "achieved": tf, "peak": peak_tf, "peak_source": peak_src + " bf16_tflops_sustained", "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,

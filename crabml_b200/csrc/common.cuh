@@ -307,6 +307,10 @@ int cc_launch_rope_exact(cc_device* dev, float* x, int64_t n_batch, int64_t batc
 int cc_launch_bmm_kcontig_exact(cc_device* dev, const float* a, const void* b, int b_dtype, float* c, int64_t ab, int64_t bb,
                                 int64_t m, int64_t k, int64_t n, int64_t sb0, int64_t sb2);
 
+// one segment of a weight row in registers: 8 x 16-byte loads + 4 f16 scales per lane (the megakernel's weight pipe; Q8_0 / Q4_0:
+// two half-group runs a, b of 4 groups; Q4_K: a = block headers, b = quants; Q6_K: a = ql, b = qh, s = d)
+struct KSeg { int4 a[4], b[4]; uint16_t s[4]; };
+
 // ---- small device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {

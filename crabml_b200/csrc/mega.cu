@@ -155,7 +155,8 @@ __device__ void phase_normq(const MkPhase& ph, float* s_red) {
 __device__ __forceinline__ int mk_dp16(const int4& w, const int4& a) {
     return __dp4a(w.x, a.x, __dp4a(w.y, a.y, __dp4a(w.z, a.z, __dp4a(w.w, a.w, 0))));
 }
-struct MkSeg { int4 a[MK_SEG], b[MK_SEG]; uint16_t s[MK_SEG]; };      // Q4_0 leaves b unused
+typedef KSeg MkSeg;                                                  // (Q4_0 leaves b unused)
+static_assert(MK_SEG == 4, "KSeg holds 4 groups");
 struct MkRowPtr { const uint8_t* q; const uint16_t* d; };
 
 template <int TYPE>
@@ -491,7 +492,7 @@ __device__ void phase_matvec(const MkPhase& ph, uint8_t* smem, float* s_w, bool 
 // shared memory: qs [k] | d [k/256] | bsums [k/16] (TKBase) | reduction scratch | f32 x
 __device__ __forceinline__ int mk_generic_sx_offset(int k) { return ((TKBase::smem_bytes(k) + 15) & ~15) + 256; }
 template <class T>
-__device__ void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, bool x_staged, const uint16_t* exp_lut, unsigned long long* stamp1) {
+__device__ void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, bool x_staged, const uint16_t* exp_lut, MkPipe& P, unsigned long long* stamp1) {
     const StreamArgs& A = ph.mv;
     const StreamMats& M = A.mats;
     const int k = A.k;
@@ -549,21 +550,29 @@ __device__ void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, float* s_
         }
         pend_row = -1;
     };
-    for (int i = 0; i < n_vrows; i++) {
-        int mat = 0, r;
+    auto locate = [&](int i, int& mat) -> int {                          // i-th virtual row of this warp -> (matrix, row)
+        int r;
+        mat = 0;
         if (pair) { mat = i & 1; r = gw + (i >> 1) * TW; }
         else {
             r = gw + i * TW;
             if (M.n > 1 && r >= M.m[0]) { r -= M.m[0]; mat = 1; if (M.n > 2 && r >= M.m[1]) { r -= M.m[1]; mat = 2; } }
         }
+        return r;
+    };
+    auto planes = [&](int mat) -> WPlanes {
         WPlanes W;
         W.p[0] = mat == 0 ? M.qs[0] : mat == 1 ? M.qs[1] : M.qs[2];
         W.p[1] = (const uint8_t*)(mat == 0 ? M.d[0] : mat == 1 ? M.d[1] : M.d[2]);
         W.p[2] = mat == 0 ? M.p2[0] : mat == 1 ? M.p2[1] : M.p2[2];
         W.p[3] = mat == 0 ? M.p3[0] : mat == 1 ? M.p3[1] : M.p3[2];
-        const float v = warp_sum(T::row_dot(W, r, k, smem, lane));
+        return W;
+    };
+    auto emit = [&](int i, float v) {                                    // row i of this warp is reduced: epilogue
+        int mat;
+        const int r = locate(i, mat);
         if (pair) {
-            if ((i & 1) == 0) { first = v; continue; }
+            if ((i & 1) == 0) { first = v; return; }
             flush_pending();
             if (lane == 0) { pend_a = first; pend_b = v; pend_row = r; pend_lut = exp_lut[f2h_bits(-first)]; }
         } else if (A.epilogue == 1) {
@@ -572,6 +581,40 @@ __device__ void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, float* s_
         } else if (lane == 0) {
             float* o = mat == 0 ? M.out[0] : mat == 1 ? M.out[1] : M.out[2];
             o[r] = v;
+        }
+    };
+    if constexpr (T::kSegmented) {
+        // rows cut into segments of 16 super-blocks; the loads of segment u + 2 are issued before segment u + 1 is consumed (two
+        // segments = 16-24 LDG.128 per lane in flight), across row boundaries
+        const int NSEG = ((k >> 8) + 15) >> 4;
+        const int U = n_vrows * NSEG;
+        KSeg& S0 = P.buf0;                                                   // the weight pipe's registers (no streaming look-ahead is pending: caller)
+        KSeg& S1 = P.buf1;
+        int x0[4] = {0, 0, 0, 0}, x1[4] = {0, 0, 0, 0};
+        int l_i = 0, l_seg = 0;
+        auto load = [&](KSeg& S, int (&x)[4], bool valid) {
+            if (valid) { int mat; const int r = locate(l_i, mat); T::seg_load(S, x, planes(mat), r, k, l_seg, lane); }
+            if (++l_seg == NSEG) { l_seg = 0; l_i++; }
+        };
+        load(S0, x0, U > 0);
+        load(S1, x1, U > 1);
+        float acc = 0.0f;
+        int c_i = 0, c_seg = 0;
+        auto finish = [&]() { if (++c_seg < NSEG) return; c_seg = 0; const float v = warp_sum(acc); acc = 0.0f; emit(c_i++, v); };
+        for (int u = 0; u < U; u += 2) {
+            acc = T::seg_dot(S0, x0, k, c_seg, smem, lane, acc);
+            finish();
+            load(S0, x0, u + 2 < U);
+            if (u + 1 >= U) break;
+            acc = T::seg_dot(S1, x1, k, c_seg, smem, lane, acc);
+            finish();
+            load(S1, x1, u + 3 < U);
+        }
+    } else {
+        for (int i = 0; i < n_vrows; i++) {
+            int mat;
+            const int r = locate(i, mat);
+            emit(i, warp_sum(T::row_dot(planes(mat), r, k, smem, lane)));
         }
     }
     flush_pending();
@@ -879,13 +922,14 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
             if (GEN && s_ph.act_type == CC_Q8_K) {   // K-quant weights: generic phase, no register look-ahead
                 unsigned long long* st1 = stamp ? prof + p * MK_PROF_SLOTS + 1 : nullptr;
                 switch (s_ph.wtype) {
-                case CC_Q2_K: phase_matvec_generic<TQ2_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
-                case CC_Q3_K: phase_matvec_generic<TQ3_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
-                case CC_Q4_K: phase_matvec_generic<TQ45_K<false>>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
-                case CC_Q5_K: phase_matvec_generic<TQ45_K<true>>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
-                case CC_Q6_K: phase_matvec_generic<TQ6_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
-                default: phase_matvec_generic<TQ8_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, st1); break;
+                case CC_Q2_K: phase_matvec_generic<TQ2_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, st1); break;
+                case CC_Q3_K: phase_matvec_generic<TQ3_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, st1); break;
+                case CC_Q4_K: phase_matvec_generic<TQ45_K<false>>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, st1); break;
+                case CC_Q5_K: phase_matvec_generic<TQ45_K<true>>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, st1); break;
+                case CC_Q6_K: phase_matvec_generic<TQ6_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, st1); break;
+                default: phase_matvec_generic<TQ8_K>(s_ph, work, s_w, wstaged == p, xstaged == p, exp_lut, pipe, st1); break;
                 }
+                prefetched = -1;              // the generic phase used the pipe's registers: a pending streaming look-ahead (mixed models) is gone
                 break;
             }
             if (prefetched != p) MK_TYPE_CALL(s_ph.wtype, matvec_prefetch<CC_Q8_0>(s_ph.mv, pipe), matvec_prefetch<CC_Q4_0>(s_ph.mv, pipe));

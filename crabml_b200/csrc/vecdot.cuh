@@ -181,6 +181,9 @@ struct KAct {
     __device__ KAct(const uint8_t* sm, int k) : q((const int4*)sm), d((const float*)(sm + al16i(k))), bs((const int16_t*)(sm + al16i(k) + al16i(k / 256 * 4))) {}
 };
 struct TKBase {
+    static constexpr bool kSegmented = false;      // overridden by the types that offer seg_load / seg_dot (Q4_K, Q6_K)
+    static __device__ __forceinline__ void seg_load(KSeg&, int (&)[4], const WPlanes&, int64_t, int, int, int) {}
+    static __device__ __forceinline__ float seg_dot(const KSeg&, const int (&)[4], int, int, const uint8_t*, int, float acc) { return acc; }
     static __host__ __device__ int smem_bytes(int k) { return al16i(k) + al16i(k / 256 * 4) + al16i(k / 16 * 2); }
     static __device__ void stage_act(const void* scratch, int64_t n_total, int bi, int k, uint8_t* sm) {
         const uint8_t* p = (const uint8_t*)scratch;
@@ -232,6 +235,47 @@ struct TQ45_K : TKBase {
         }
         return acc;
     }
+    // ---- the same dot cut into SEGMENTS of 16 super-blocks (4 iterations of the loop above) whose 8 16-byte loads are issued as one
+    // batch into a KSeg, so a caller can keep the next segment in flight while it computes the current one (megakernel generic
+    // phase).  Per lane the terms are added in the same order as in row_dot -> identical bits.  x: 4 extra words per segment (Q6_K).
+    static constexpr bool kSegmented = !FIVE;          // Q5_K would need 4 more 16-byte registers per segment (qh): plain loop
+    static __device__ __forceinline__ void seg_load(KSeg& S, int (&x)[4], const WPlanes& W, int64_t row, int k, int seg, int lane) {
+        const int nsb = k >> 8, BB = 144, QOFF = 16;
+        const uint8_t* wrow = W.p[0] + row * (int64_t)nsb * BB;
+        const int j = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int sb = seg * 16 + it * 4 + (lane >> 3);
+            if (sb < nsb) {
+                const uint8_t* blk = wrow + (int64_t)sb * BB;
+                S.a[it] = ld_stream_16(blk);
+                S.b[it] = ld_stream_16(blk + QOFF + 16 * j);
+            }
+        }
+    }
+    static __device__ __forceinline__ float seg_dot(const KSeg& S, const int (&x)[4], int k, int seg, const uint8_t* sm, int lane, float acc) {
+        const int nsb = k >> 8;
+        KAct A(sm, k);
+        const int j = lane & 7, g = j >> 1;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int sb = seg * 16 + it * 4 + (lane >> 3);
+            if (sb < nsb) {
+                const int4 hdr = S.a[it], q = S.b[it];
+                unsigned s0, s1, m0, m1;
+                k4_unpack((unsigned)hdr.y, (unsigned)hdr.z, (unsigned)hdr.w, s0, s1, m0, m1);
+                int4 lo = and4(q, 0x0F0F0F0F), hi = shr4(q, 4, 0x0F0F0F0F);
+                const int abase = sb * 16 + g * 4 + (j & 1);
+                int sum_lo = dot16(lo, A.q[abase]), sum_hi = dot16(hi, A.q[abase + 2]);
+                int isum = byte_of(s0, s1, 2 * g) * sum_lo + byte_of(s0, s1, 2 * g + 1) * sum_hi;
+                int msum = ((int)A.bs[sb * 16 + 2 * j] + (int)A.bs[sb * 16 + 2 * j + 1]) * byte_of(m0, m1, j);
+                float da = A.d[sb];
+                float d = h2f_bits((uint16_t)(hdr.x & 0xFFFF)) * da, dmin = h2f_bits((uint16_t)((unsigned)hdr.x >> 16)) * da;
+                acc += d * (float)isum - dmin * (float)msum;
+            }
+        }
+        return acc;
+    }
 };
 
 // Q6_K: buf_q6_k.rs:183-235.  8 lanes per super-block, lane j owns ql chunk j.
@@ -256,6 +300,48 @@ struct TQ6_K : TKBase {
             int s_hi = dot16(hi, A.q[a_hi]) - 32 * (int)A.bs[a_hi];
             int isum = (int)sc[sb * 16 + (e_lo >> 4)] * s_lo + (int)sc[sb * 16 + (e_lo >> 4) + 4] * s_hi;
             acc += (float)isum * (h2f_bits(wd[sb]) * A.d[sb]);
+        }
+        return acc;
+    }
+    // segments of 16 super-blocks, loads batched (see TQ45_K): ql chunk, qh chunk, the two sub-block scales and d per iteration
+    static constexpr bool kSegmented = true;
+    static __device__ __forceinline__ void seg_load(KSeg& S, int (&x)[4], const WPlanes& W, int64_t row, int k, int seg, int lane) {
+        const int nsb = k >> 8;
+        const uint8_t* ql = W.p[0] + row * (int64_t)nsb * 128;
+        const uint8_t* qh = W.p[1] + row * (int64_t)nsb * 64;
+        const int8_t* sc = (const int8_t*)W.p[2] + row * (int64_t)nsb * 16;
+        const uint16_t* wd = (const uint16_t*)W.p[3] + row * (int64_t)nsb;
+        const int j = lane & 7, n = j >> 2, jj = j & 3, r = jj & 1, p = jj >> 1;
+        const int e_lo = 128 * n + 32 * p + 16 * r;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int sb = seg * 16 + it * 4 + (lane >> 3);
+            if (sb < nsb) {
+                S.a[it] = ld_stream_16(ql + (int64_t)sb * 128 + 16 * j);
+                S.b[it] = ld_stream_16(qh + (int64_t)sb * 64 + 32 * n + 16 * r);
+                x[it] = ((int)sc[sb * 16 + (e_lo >> 4)] & 0xFFFF) | ((int)sc[sb * 16 + (e_lo >> 4) + 4] << 16);     // the two sub-block scales
+                S.s[it] = wd[sb];
+            }
+        }
+    }
+    static __device__ __forceinline__ float seg_dot(const KSeg& S, const int (&x)[4], int k, int seg, const uint8_t* sm, int lane, float acc) {
+        const int nsb = k >> 8;
+        KAct A(sm, k);
+        const int j = lane & 7, n = j >> 2, jj = j & 3, r = jj & 1, p = jj >> 1;
+        const int e_lo = 128 * n + 32 * p + 16 * r;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int sb = seg * 16 + it * 4 + (lane >> 3);
+            if (sb < nsb) {
+                const int4 l = S.a[it], h = S.b[it];
+                int4 lo = or4(and4(l, 0x0F0F0F0F), shl4(shr4(h, 2 * p, 0x03030303), 4));
+                int4 hi = or4(shr4(l, 4, 0x0F0F0F0F), shl4(shr4(h, 2 * p + 4, 0x03030303), 4));
+                const int a_lo = sb * 16 + (e_lo >> 4), a_hi = a_lo + 4;
+                int s_lo = dot16(lo, A.q[a_lo]) - 32 * (int)A.bs[a_lo];
+                int s_hi = dot16(hi, A.q[a_hi]) - 32 * (int)A.bs[a_hi];
+                int isum = (int)(int16_t)(x[it] & 0xFFFF) * s_lo + (x[it] >> 16) * s_hi;
+                acc += (float)isum * (h2f_bits(S.s[it]) * A.d[sb]);
+            }
         }
         return acc;
     }

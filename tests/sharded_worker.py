@@ -102,10 +102,13 @@ def run_cpu(rank, world):
     return 0
 
 
-def run_gpu(rank, world, transports):
+def run_gpu(rank, world, transports, one_gpu=False):
+    """one_gpu: every rank is its own PROCESS on cuda:0 (the contexts are time-sliced, the peers' windows are mapped through CUDA IPC
+    exactly as across GPUs): the real multi-process protocol where only one GPU is available."""
     from crabml_b200 import CudaTensor, CudaTensorDevice, capi
     from crabml_b200 import runner as R
-    torch.cuda.set_device(rank)
+    gpu = 0 if one_gpu else rank
+    torch.cuda.set_device(gpu)
 
     def exchange(blob):
         out = [None] * world
@@ -113,7 +116,7 @@ def run_gpu(rank, world, transports):
         return out
     # ---- 1. the two exchange ops, eager: bit-exact against a rank-ordered numpy sum ------------------------------------
     for transport in transports:
-        dev = CudaTensorDevice(rank)
+        dev = CudaTensorDevice(gpu)
         dev.init_comm(rank, world, exchange, transport)
         for n in (4096, 32, 32768):
             for rep in range(3):
@@ -137,24 +140,27 @@ def run_gpu(rank, world, transports):
     tokens = [1, 777, 31999, 5, 6, 7]
     want = None
     if rank == 0:
-        dev = CudaTensorDevice(rank, lazy=0)
+        dev = CudaTensorDevice(gpu, lazy=0)
         w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=7)
         r = R.LlamaRunner(dev, conf, w, 16)
         want = np.stack([r.forward([t], p).copy() for p, t in enumerate(tokens)])
         r.close(); del w; dev.close()
     plan = sharding.make_plan(conf.n_heads, conf.n_kv_heads, conf.embedding_dim, conf.hidden_dim, conf.vocab_size, capi.Q8_0, rank, world)
     results = {}
+    modes_seen = {}
     for transport, lazy in [(t, l) for t in transports for l in ((0, 1, 2) if t == "p2p" else (0, 1))]:
-        dev = CudaTensorDevice(rank, lazy=lazy)
+        dev = CudaTensorDevice(gpu, lazy=lazy)
         dev.init_comm(rank, world, exchange, transport)
         w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=7, plan=plan)
         r = R.LlamaRunner(dev, conf, w, 16, plan=plan)
         got = np.stack([r.forward([t], p).copy() for p, t in enumerate(tokens)])
         assert np.isfinite(got).all()
-        ref = torch.from_numpy(got.copy()).cuda()
+        ref = torch.from_numpy(got.copy()) if one_gpu else torch.from_numpy(got.copy()).cuda()
         dist.broadcast(ref, 0)
         if transport == "p2p":
             assert np.array_equal(ref.cpu().numpy().view(np.uint32), got.view(np.uint32)), ("ranks diverged", transport, lazy)
+        if one_gpu and rank == 0:
+            modes_seen.setdefault(transport, []).append(got)
         if lazy:
             st = dev.lazy_stats()
             assert st["uncached"] == 0 and st["graph_replays"] >= 2, st
@@ -165,6 +171,9 @@ def run_gpu(rank, world, transports):
         dist.barrier()
         r.close(); del w; dev.close()
     if rank == 0:
+        for transport, outs in modes_seen.items():          # eager, CUDA-graph and megakernel runs of the sharded model agree bit for bit
+            for o in outs[1:]:
+                assert np.array_equal(o.view(np.uint32), outs[0].view(np.uint32)), "execution modes of the sharded run differ"
         print("sharded parity vs single GPU (max rel):", results, flush=True)
     return 0
 
@@ -173,15 +182,20 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", choices=["cpu", "gpu"], required=True)
     ap.add_argument("--transports", default="p2p,nccl")
+    ap.add_argument("--one-gpu", action="store_true", help="every rank is a process on cuda:0 (gloo rendezvous, p2p transport through CUDA IPC)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     if a.mode == "cpu":
         dist.init_process_group("gloo", rank=rank, world_size=world)
         rc = run_cpu(rank, world)
     else:
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
-        rc = run_gpu(rank, world, a.transports.split(","))
+        if a.one_gpu:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+            rc = run_gpu(rank, world, ["p2p"], one_gpu=True)
+        else:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+            dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+            rc = run_gpu(rank, world, a.transports.split(","))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(rc)

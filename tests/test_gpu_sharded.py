@@ -117,13 +117,16 @@ def _world_of_two_on_one_gpu(lazy):
     return devs
 
 
-@pytest.mark.parametrize("lazy", [0, 1, 2])
+@pytest.mark.parametrize("lazy", [0])
 def test_world_of_two_on_one_gpu_exchange_is_the_rank_ordered_sum(lazy):
     """The REAL two-rank protocol on a single GPU (two devices of this process, half of the SMs each, windows wired in process):
     column-split matvec -> all_reduce (+ residual) and row-split matvec -> all_gather in every execution mode, including the
     exchange fused into the megakernel (coalesced peer stores from the matvec epilogue, handshake on the grid barrier, reduction in
     the consumer's prologue).  Expected = the partial rows of the eager single-device kernels added in rank order, bit for bit, and
-    both ranks must hold identical bits."""
+    both ranks must hold identical bits.
+    In-process ranks share one CUDA context, where graph instantiation / first-use allocations of one rank can wait for the other
+    rank's spinning exchange kernel: this in-process form runs the eager mode only; the CUDA-graph and megakernel modes of the
+    two-rank protocol run as two PROCESSES on the one GPU (test_two_processes_on_one_gpu_sharded_llama below)."""
     from crabml_b200 import CudaTensor, capi
     from crabml_b200.runner import synth_scale
     k, m = 4096, 4096
@@ -186,48 +189,14 @@ def test_world_of_two_on_one_gpu_exchange_is_the_rank_ordered_sum(lazy):
             d.close()
 
 
-@pytest.mark.parametrize("lazy", [1, 2])
-def test_world_of_two_on_one_gpu_sharded_llama(lazy):
-    """A 2-layer Llama-2-7B-shaped model sharded over the two in-process ranks (rows of wq/wk/wv/gate/up/classifier, block columns of
-    wo/down): both ranks produce bit-identical logits, equal to the eager sharded run, and close to the unsharded model (the
-    exchange changes the association of the row sums: (a0 + a1) instead of one 4096-long dot)."""
-    from crabml_b200 import capi, sharding
-    from crabml_b200 import runner as R
-    conf = R.LlamaConfig(32, 32, 2, 4096, 11008, 4096, 32000, 1e-5, 128)
-    toks = [1, 777, 31999, 5]
-
-    def sharded_logits(mode):
-        devs = _world_of_two_on_one_gpu(mode)
-        try:
-            # weights and runners first, on the main thread (allocation / free of non-pooled buffers waits for the whole context: it
-            # must not happen while the other in-process rank is already spinning in an exchange)
-            runners = []
-            for r in range(2):
-                plan = sharding.make_plan(conf.n_heads, conf.n_kv_heads, conf.embedding_dim, conf.hidden_dim, conf.vocab_size, capi.Q8_0, r, 2)
-                w = R.synthetic_weights(devs[r], conf, capi.Q8_0, capi.Q8_0, seed=7, plan=plan)
-                runners.append(R.LlamaRunner(devs[r], conf, w, 16, plan=plan))
-                devs[r].synchronize()
-
-            def rank_fn(r):
-                return lambda: np.stack([runners[r].forward([t], p).copy() for p, t in enumerate(toks)])
-            out = _run_ranks([rank_fn(0), rank_fn(1)])
-            for rr in runners:
-                rr.close()
-            return out
-        finally:
-            for d in devs:
-                d.close()
-    got = sharded_logits(lazy)
-    np.testing.assert_array_equal(got[0].view(np.uint32), got[1].view(np.uint32), err_msg="ranks disagree")
-    eager = sharded_logits(0)
-    np.testing.assert_array_equal(got[0].view(np.uint32), eager[0].view(np.uint32), err_msg=f"lazy={lazy} vs eager sharded run")
-    dev = make_device(lazy=lazy)
-    try:
-        w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=7)
-        r1 = R.LlamaRunner(dev, conf, w, 16)
-        single = np.stack([r1.forward([t], p).copy() for p, t in enumerate(toks)])
-        r1.close()
-    finally:
-        dev.close()
-    rel = float(np.abs(got[0] - single).max() / np.abs(single).max())
-    assert rel < 3e-2, rel
+def test_two_processes_on_one_gpu_sharded_llama():
+    """World of 2 on ONE GPU, one process per rank (time-sliced contexts, peers' windows mapped through CUDA IPC exactly as across
+    GPUs): the exchange ops bit-exact against the rank-ordered numpy sum, and the 2-layer Llama-2-7B-shaped sharded model in the
+    eager, CUDA-graph and megakernel modes -- ranks bit-identical, modes bit-identical, close to the unsharded logits.
+    This is the multi-GPU path's parity test on a single-GPU lease (tests/sharded_worker.py --one-gpu)."""
+    n = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "sharded_worker.py"), "--mode", "gpu", "--one-gpu"]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
+    assert "sharded parity vs single GPU" in p.stdout

@@ -9,7 +9,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__t_bytes.sum", "lts__t_bytes.sum",
-        "sm__inst_executed.sum", "smsp__cycles_active.avg"]
+        "sm__inst_executed.sum", "smsp__cycles_active.avg", "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_src_fp16_dst_fp32.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]
 
 for path in sys.argv[1:]:
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -22,5 +23,5 @@ for path in sys.argv[1:]:
         u = dict(zip(hdr, units))
         print(f"== {path}: {d.get('Kernel Name', '?')[:90]}")
         for k in hdr:
-            if k in WANT or "tensor" in k and "pct" in k:
+            if k in WANT:
                 print(f"   {k:75s} {d[k]:>16s} {u[k]}")
