@@ -78,29 +78,33 @@ __host__ __device__ constexpr unsigned pg_instr_desc(int umma_m, int umma_n) {
 }
 
 struct PgShared {
-    unsigned long long full[PG_STAGES], empty[PG_STAGES], tmem_full;
+    unsigned long long full[PG_STAGES], empty[PG_STAGES], tmem_full;      // (3 or PG_STAGES slots in use)
     unsigned tmem_base;
 };
 
-// grid: (ceil(m / 128), ceil(b / BLOCK_N)); dynamic smem: 1024-aligned ring of PG_STAGES x (A tile 16 KB + B tile BLOCK_N*128 B)
-template <int BLOCK_N>
+// grid: (ceil(m / (128 * MT)), ceil(b / BLOCK_N)); dynamic smem: 1024-aligned ring of STAGES x (A tile MT x 16 KB + B tile BLOCK_N*128 B)
+// MT = 2: the CTA owns a 256-row weight tile as TWO M = 128 accumulators (2 x BLOCK_N TMEM columns) that share every B tile -- 1.5x
+// fewer operand bytes per FLOP than 128 x 256 tiles, which matters because 148 CTAs pulling 48 KB per 128x256x64 step ask more of L2
+// than it delivers (profiles/r02e: 47 % tensor pipe with MT = 1).
+template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(PG_THREADS, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                                                                   float* __restrict__ C, int m, int b, int k) {
     extern __shared__ __align__(1024) uint8_t pg_smem_raw[];
     __shared__ PgShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr unsigned A_BYTES = PG_BLOCK_M * PG_BLOCK_K * 2, B_BYTES = BLOCK_N * PG_BLOCK_K * 2;
-    constexpr unsigned TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;           // power of two >= 32
+    constexpr unsigned A_TILE = PG_BLOCK_M * PG_BLOCK_K * 2, A_BYTES = MT * A_TILE, B_BYTES = BLOCK_N * PG_BLOCK_K * 2;
+    constexpr unsigned TMEM_COLS = MT * BLOCK_N < 32 ? 32 : MT * BLOCK_N;     // power of two >= 32 (64 .. 512)
+    constexpr int STAGES = (A_BYTES + B_BYTES) * PG_STAGES <= 200 * 1024 ? PG_STAGES : 3;
     uint8_t* ring = (uint8_t*)(((uintptr_t)pg_smem_raw + 1023) & ~(uintptr_t)1023);
     const int num_kb = k / PG_BLOCK_K;
-    const int m0 = blockIdx.x * PG_BLOCK_M, n0 = blockIdx.y * BLOCK_N;
+    const int m0 = blockIdx.x * PG_BLOCK_M * MT, n0 = blockIdx.y * BLOCK_N;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < PG_STAGES; s++) { pg_mbar_init(pg_smem(&sh.full[s]), 1); pg_mbar_init(pg_smem(&sh.empty[s]), 1); }
+        for (int s = 0; s < STAGES; s++) { pg_mbar_init(pg_smem(&sh.full[s]), 1); pg_mbar_init(pg_smem(&sh.empty[s]), 1); }
         pg_mbar_init(pg_smem(&sh.tmem_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -117,13 +121,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) umma_gemm_kernel(const __grid_c
         // ===== TMA producer =====
         if (lane == 0) {
             for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % PG_STAGES;
-                const unsigned ph = (unsigned)(kb / PG_STAGES) & 1u;
+                const int s = kb % STAGES;
+                const unsigned ph = (unsigned)(kb / STAGES) & 1u;
                 pg_mbar_wait(pg_smem(&sh.empty[s]), ph ^ 1u);           // slot free (passes at once on the first round)
                 const unsigned full = pg_smem(&sh.full[s]);
                 pg_mbar_expect_tx(full, A_BYTES + B_BYTES);
                 uint8_t* st = ring + (size_t)s * (A_BYTES + B_BYTES);
-                pg_tma_load_2d(pg_smem(st), &tmap_w, full, kb * PG_BLOCK_K, m0);
+#pragma unroll
+                for (int t = 0; t < MT; t++) pg_tma_load_2d(pg_smem(st + t * A_TILE), &tmap_w, full, kb * PG_BLOCK_K, m0 + t * PG_BLOCK_M);
                 pg_tma_load_2d(pg_smem(st + A_BYTES), &tmap_x, full, kb * PG_BLOCK_K, n0);
             }
         }
@@ -132,17 +137,21 @@ __global__ void __launch_bounds__(PG_THREADS, 1) umma_gemm_kernel(const __grid_c
         if (lane == 0) {
             constexpr unsigned idesc = pg_instr_desc(PG_BLOCK_M, BLOCK_N);
             for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % PG_STAGES;
-                const unsigned ph = (unsigned)(kb / PG_STAGES) & 1u;
+                const int s = kb % STAGES;
+                const unsigned ph = (unsigned)(kb / STAGES) & 1u;
                 pg_mbar_wait(pg_smem(&sh.full[s]), ph);                  // TMA landed this stage
                 pg_fence_after();
                 uint8_t* st = ring + (size_t)s * (A_BYTES + B_BYTES);
-                const uint64_t da = pg_smem_desc(pg_smem(st)), db = pg_smem_desc(pg_smem(st + A_BYTES));
+                const uint64_t db = pg_smem_desc(pg_smem(st + A_BYTES));
 #pragma unroll
-                for (int kk = 0; kk < PG_BLOCK_K / PG_UMMA_K; kk++) {
-                    // advancing K inside the 128-byte swizzle atom = advancing the (pre-swizzle) start address by 32 bytes
-                    const uint64_t adv = (uint64_t)((kk * PG_UMMA_K * 2) >> 4);
-                    pg_umma_f16(tmem_acc, da + adv, db + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                for (int t = 0; t < MT; t++) {
+                    const uint64_t da = pg_smem_desc(pg_smem(st + t * A_TILE));
+#pragma unroll
+                    for (int kk = 0; kk < PG_BLOCK_K / PG_UMMA_K; kk++) {
+                        // advancing K inside the 128-byte swizzle atom = advancing the (pre-swizzle) start address by 32 bytes
+                        const uint64_t adv = (uint64_t)((kk * PG_UMMA_K * 2) >> 4);
+                        pg_umma_f16(tmem_acc + (unsigned)(t * BLOCK_N), da + adv, db + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                    }
                 }
                 pg_umma_commit(pg_smem(&sh.empty[s]));                   // frees the slot once these MMAs have read it
             }
@@ -153,11 +162,12 @@ __global__ void __launch_bounds__(PG_THREADS, 1) umma_gemm_kernel(const __grid_c
         const int q = warp & 3;                                          // a warp reads the TMEM lanes 32 * (warp % 4) ..
         pg_mbar_wait(pg_smem(&sh.tmem_full), 0);
         pg_fence_after();
-        const int row = m0 + q * 32 + lane;                              // weight row = output column index
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int cc = 0; cc < MT * BLOCK_N; cc += 32) {
+            const int t = cc / BLOCK_N, c0 = cc - t * BLOCK_N;          // accumulator t holds the weight rows m0 + 128 t ..
+            const int row = m0 + t * PG_BLOCK_M + q * 32 + lane;         // weight row = output column index
             unsigned v[32];
-            const unsigned taddr = tmem_acc + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+            const unsigned taddr = tmem_acc + ((unsigned)(q * 32) << 16) + (unsigned)cc;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
                 "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -262,12 +272,14 @@ bool cc_prefill_supported(int wtype, int64_t m, int64_t k, int64_t b) {
     return b >= min_b && k % PG_BLOCK_K == 0 && k >= PG_BLOCK_K && m >= 1 && (at == CC_Q8_0 || at == CC_Q8_K);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 static int pg_launch(cc_device* dev, const CUtensorMap& tw, const CUtensorMap& tx, float* out, int64_t m, int64_t b, int64_t k) {
-    const size_t smem = (size_t)PG_STAGES * (PG_BLOCK_M * PG_BLOCK_K * 2 + BLOCK_N * PG_BLOCK_K * 2) + 1024;
-    CC_CUDA(dev, cudaFuncSetAttribute(umma_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((m + PG_BLOCK_M - 1) / PG_BLOCK_M), (unsigned)((b + BLOCK_N - 1) / BLOCK_N));
-    umma_gemm_kernel<BLOCK_N><<<grid, PG_THREADS, smem, dev->stream>>>(tw, tx, out, (int)m, (int)b, (int)k);
+    const size_t stage = (size_t)MT * PG_BLOCK_M * PG_BLOCK_K * 2 + (size_t)BLOCK_N * PG_BLOCK_K * 2;
+    const int stages = stage * PG_STAGES <= 200 * 1024 ? PG_STAGES : 3;
+    const size_t smem = (size_t)stages * stage + 1024;
+    CC_CUDA(dev, cudaFuncSetAttribute(umma_gemm_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((m + PG_BLOCK_M * MT - 1) / (PG_BLOCK_M * MT)), (unsigned)((b + BLOCK_N - 1) / BLOCK_N));
+    umma_gemm_kernel<BLOCK_N, MT><<<grid, PG_THREADS, smem, dev->stream>>>(tw, tx, out, (int)m, (int)b, (int)k);
     CC_LAUNCH_CHECK(dev);
     return CC_OK;
 }
@@ -314,7 +326,9 @@ int cc_launch_prefill_matmul(cc_device* dev, const cc_buf* w, const void* act_q8
     if (rc) return rc;
     rc = pg_make_tmap(dev, &tx, s->x, b, k, block_n);
     if (rc) return rc;
-    if (block_n == 256) return pg_launch<256>(dev, tw, tx, out, m, b, k);
-    if (block_n == 128) return pg_launch<128>(dev, tw, tx, out, m, b, k);
-    return pg_launch<64>(dev, tw, tx, out, m, b, k);
+    static const bool one_tile = getenv("CRABML_PREFILL_MT1") != nullptr;          // developer A/B: 128-row CTA tiles
+    const bool mt2 = !one_tile && m >= 512;
+    if (block_n == 256) return mt2 ? pg_launch<256, 2>(dev, tw, tx, out, m, b, k) : pg_launch<256, 1>(dev, tw, tx, out, m, b, k);
+    if (block_n == 128) return mt2 ? pg_launch<128, 2>(dev, tw, tx, out, m, b, k) : pg_launch<128, 1>(dev, tw, tx, out, m, b, k);
+    return mt2 ? pg_launch<64, 2>(dev, tw, tx, out, m, b, k) : pg_launch<64, 1>(dev, tw, tx, out, m, b, k);
 }

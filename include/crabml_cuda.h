@@ -170,7 +170,9 @@ CC_API int cc_test_quantize_activation(cc_device* dev, const cc_view* x, int32_t
  * cc_comm_connect.  cc_comm_init_nccl switches the transport to NCCL (baseline; id from cc_comm_nccl_unique_id on rank 0). */
 CC_API int cc_comm_create(cc_device* dev, int32_t rank, int32_t world, uint8_t* handle_out_64);
 CC_API int cc_comm_connect(cc_device* dev, const uint8_t* handles_world_x_64);
-/* ranks that are devices of ONE process (peers[r] = the cc_device of rank r): windows are wired directly, no IPC handles */
+/* ranks that are devices of ONE process, one per GPU (peers[r] = the cc_device of rank r): windows are wired directly, no IPC handles.
+ * NOTE: ranks of one process share a CUDA context per GPU; put them on DIFFERENT GPUs -- on the same GPU a context-wide wait of one rank
+ * (first-use allocation, module load, cudaFree) can deadlock against the other rank's spinning exchange. */
 CC_API int cc_comm_connect_local(cc_device* dev, cc_device* const* peers);
 CC_API int cc_comm_nccl_unique_id(cc_device* dev, uint8_t* id_out_128);
 CC_API int cc_comm_init_nccl(cc_device* dev, const uint8_t* id_128);

@@ -74,6 +74,14 @@ def test_prefill_dense_7b_shapes(gdev, t):
     print("prefill error / budget:", r1, r2)
 
 
+def test_prefill_dense_256_row_cta_tiles(gdev):
+    # m >= 512: a CTA owns 256 weight rows as two M = 128 accumulators sharing every activation tile; ragged second tile (640 = 2 x 256
+    # + 128, 1000 = 3 x 256 + 232) and all three N tiles
+    run_dense(gdev, oc.Q8_0, 640, 512, 64, seed=81)
+    run_dense(gdev, oc.Q8_0, 1000, 1024, 130, seed=82)
+    run_dense(gdev, oc.Q4_0, 1024, 2048, 300, seed=83)
+
+
 def test_prefill_small_batches_keep_the_exact_block_path(gdev):
     """b below the dense threshold still takes the per-row quantised dot (1e-6 * sum|terms| parity, test_gpu_matvec.py)"""
     from tests.test_gpu_matvec import run_case
