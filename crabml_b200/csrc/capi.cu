@@ -380,7 +380,8 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
     if (rc) return rc;
     if (LAZY(dev)) { *out = c; return cc_lazy_record(dev, L_MATVEC, w, x, c, 0, 0, 0, 0, nullptr, 0); }
     const float* xf = (const float*)x->buf->plane[0];
-    if (at != CC_F32) {
+    const bool dense = !dev->exact && !(b == 1 && cc_stream_supported(wt, k)) && cc_prefill_supported(wt, m, k, b);      // tensor-core path (prefill_gemm.cu)
+    if (at != CC_F32 && !(dense && at == CC_Q8_0)) {         // (the dense path quantises Q8_0 partners itself, fused with the f16 conversion)
         rc = cc_ensure_act_scratch(dev, cc_act_bytes(at, b * k));
         if (!rc) rc = cc_launch_quantize(dev, xf, b * k, at, dev->act_scratch);     // matmul_vec.rs:37-40
     }
@@ -398,8 +399,8 @@ extern "C" CC_API int cc_matmul_vec(cc_device* dev, const cc_view* w, const cc_v
         if (blocks) cc_pool_free(dev, blocks, cls);
     } else if (!rc && b == 1 && cc_stream_supported(wt, k)) {
         rc = cc_launch_matvec_stream_plain(dev, w->buf, dev->act_scratch, (float*)c->base, m, k);     // decode hot path
-    } else if (!rc && cc_prefill_supported(wt, m, k, b)) {
-        rc = cc_launch_prefill_matmul(dev, w->buf, dev->act_scratch, (float*)c->base, m, k, b);       // prefill: dense, tensor cores
+    } else if (!rc && dense) {
+        rc = cc_launch_prefill_matmul(dev, w->buf, dev->act_scratch, at == CC_Q8_0 ? xf : nullptr, (float*)c->base, m, k, b);       // prefill: dense, tensor cores
     } else if (!rc) rc = cc_launch_matvec(dev, w->buf, dev->act_scratch, xf, (float*)c->base, m, k, b);
     if (rc) { cc_tensor_release(c); return rc; }
     *out = c;

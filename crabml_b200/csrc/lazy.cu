@@ -239,10 +239,11 @@ struct Fuser {
                 const int wt = a.buf->dtype, at = cc_partner_type(wt);
                 const float* xf = (const float*)b.buf->plane[0];
                 int rc = CC_OK;
-                if (at != CC_F32) rc = cc_launch_quantize(d, xf, bb * k, at, d->act_scratch);
+                const bool dense = !(bb == 1 && cc_stream_supported(wt, k)) && cc_prefill_supported(wt, m, k, bb);
+                if (at != CC_F32 && !(dense && at == CC_Q8_0)) rc = cc_launch_quantize(d, xf, bb * k, at, d->act_scratch);
                 if (rc) return rc;
                 if (bb == 1 && cc_stream_supported(wt, k)) return cc_launch_matvec_stream_plain(d, a.buf, d->act_scratch, (float*)op.out->base, m, k);
-                if (cc_prefill_supported(wt, m, k, bb)) return cc_launch_prefill_matmul(d, a.buf, d->act_scratch, (float*)op.out->base, m, k, bb);
+                if (dense) return cc_launch_prefill_matmul(d, a.buf, d->act_scratch, at == CC_Q8_0 ? xf : nullptr, (float*)op.out->base, m, k, bb);
                 return cc_launch_matvec(d, a.buf, d->act_scratch, xf, (float*)op.out->base, m, k, bb);
             }
             }

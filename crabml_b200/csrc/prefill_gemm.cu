@@ -217,6 +217,20 @@ __global__ void act_q8k_to_f16_kernel(ActQ8_K act, int64_t nelems, __half* __res
     *(__half2*)(out + i) = __halves2half2(__float2half_rn((float)act.qs[i] * d), __float2half_rn((float)act.qs[i + 1] * d));
 }
 
+// f32 activation rows -> f16(q * d) in ONE pass (what quantize_q8_0_kernel + act_q8_to_f16_kernel produce together, same arithmetic:
+// d = max|x| / 127, q = trunc(x / d), stored scale f32(f16(d)); buf_q8_0.rs:87-134): one warp per 32-element block
+__global__ void act_f32_to_q8f16_kernel(const float* __restrict__ x, int64_t nblocks, __half* __restrict__ out) {
+    const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= nblocks) return;
+    const float v = x[b * 32 + lane];
+    const float amax = warp_max(fabsf(v));
+    const float d = amax / 127.0f;
+    const int q = __float2int_rz(v / d);                       // NaN (0 / 0) -> 0
+    const float d16 = __half2float(__float2half_rn(d));
+    out[b * 32 + lane] = __float2half_rn((float)(int)(int8_t)q * d16);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -306,8 +320,9 @@ static int pg_weight_f16(cc_device* dev, const cc_buf* w, int64_t m, int64_t k, 
     return CC_OK;
 }
 
-// act: the quantisation of the (b, k) activation to the weight's partner type, Q8_0 or Q8_K (quantize.cu layout); out: f32 [b][m]
-int cc_launch_prefill_matmul(cc_device* dev, const cc_buf* w, const void* act_q8_0, float* out, int64_t m, int64_t k, int64_t b) {
+// act: the quantisation of the (b, k) activation to the weight's partner type, Q8_0 or Q8_K (quantize.cu layout) -- or, for Q8_0
+// partners, x_f32: the f32 activation itself, quantised on the way to f16 (the caller then skips its own quantise launch); out: f32 [b][m]
+int cc_launch_prefill_matmul(cc_device* dev, const cc_buf* w, const void* act_q8_0, const float* x_f32, float* out, int64_t m, int64_t k, int64_t b) {
     PgScratch* s = pg_scratch(dev);
     const void* wf16 = nullptr;
     int rc = pg_weight_f16(dev, w, m, k, s, &wf16);
@@ -317,6 +332,7 @@ int cc_launch_prefill_matmul(cc_device* dev, const cc_buf* w, const void* act_q8
     {
         const int64_t na = b * k;
         if (cc_partner_type(w->dtype) == CC_Q8_K) act_q8k_to_f16_kernel<<<(unsigned)((na / 2 + 255) / 256), 256, 0, dev->stream>>>(cc_act_q8_k((void*)act_q8_0, na), na, (__half*)s->x);
+        else if (x_f32) act_f32_to_q8f16_kernel<<<(unsigned)((na / 32 + 7) / 8), 256, 0, dev->stream>>>(x_f32, na / 32, (__half*)s->x);      // quantise + f16 in one pass
         else act_q8_to_f16_kernel<<<(unsigned)((na / 2 + 255) / 256), 256, 0, dev->stream>>>(cc_act_q8_0((void*)act_q8_0, na), na, (__half*)s->x);
         CC_LAUNCH_CHECK(dev);
     }

@@ -48,6 +48,7 @@ def layer(T, dev, w, kc, vc, token, pos, tap):
     q = q.reshape([1, HEADS, HD]).transpose([1, 0, 2]).contiguous().scale_inplace(1.0 / np.sqrt(np.float32(HD)))
     att = q.batch_matmul(kc.transpose([0, 2, 1])).softmax_inplace(2)
     a = att.batch_matmul(vc).reshape([1, DIM])
+    del q, k, v, att          # like the moves of the Rust / C++ runner: the fuser only folds intermediates nobody else can observe
     a = tap("att", a)
     o = w["wo"].matmul_vec(a)
     o = tap("o", o)
@@ -59,6 +60,7 @@ def layer(T, dev, w, kc, vc, token, pos, tap):
     g, u = w["gate"].matmul_vec(x), w["up"].matmul_vec(x)
     g, u = tap("g", g), tap("u", u)
     h = g.silu_inplace().mul_inplace(u)
+    del g, u
     h = tap("h", h)
     y = w["down"].matmul_vec(h)
     y = tap("y", y)
