@@ -47,14 +47,15 @@ def declared_symbols():
 
 class ccr_llama_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_heads", "n_kv_heads", "n_layers", "embedding_dim", "hidden_dim", "seq_len", "vocab_size", "rope_dim")] + \
-               [("rms_norm_eps", C.c_float), ("use_f16_kv_cache", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("hidden_local", C.c_int32)]
+               [("rms_norm_eps", C.c_float), ("use_f16_kv_cache", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("hidden_local", C.c_int32),
+                ("arch", C.c_int32)]
 
 
 class ccr_llama_weights(C.Structure):
     _pp = C.POINTER(C.c_void_p)
     _fields_ = [("token_embed", C.c_void_p), ("wq", _pp), ("wk", _pp), ("wv", _pp), ("wo", _pp), ("ffn_gate", _pp),
                 ("ffn_down", _pp), ("ffn_up", _pp), ("rms_att", _pp), ("rms_ffn", _pp), ("rms_final", C.c_void_p),
-                ("output_weight", C.c_void_p)]
+                ("output_weight", C.c_void_p), ("bq", _pp), ("bk", _pp), ("bv", _pp)]
 
 
 _lib = None

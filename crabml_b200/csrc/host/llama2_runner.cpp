@@ -18,7 +18,7 @@ struct ccr_runner {
     cc_device* dev = nullptr;
     ccr_llama_config conf{};
     CudaTensor token_embed, rms_final, output_weight;
-    std::vector<CudaTensor> wq, wk, wv, wo, ffn_gate, ffn_down, ffn_up, rms_att, rms_ffn;
+    std::vector<CudaTensor> wq, wk, wv, wo, ffn_gate, ffn_down, ffn_up, rms_att, rms_ffn, bq, bk, bv;
     std::vector<CudaTensor> key_cache, value_cache;       // (layer) x [n_kv_heads, seq, head_dim]
     std::vector<float> logits;
     float* pinned_logits = nullptr;       // staging ring of the asynchronous logits export (generate_greedy_ex), grown on demand
@@ -36,10 +36,13 @@ struct ccr_runner {
     int64_t kv_cache_len() const { return key_cache[0].shape()[1]; }
 
     CudaTensor forward_llama(const std::vector<int64_t>& tokens, int64_t pos, int slot = -1);
+    CudaTensor forward_arch(const std::vector<int64_t>& tokens, int64_t pos, int slot = -1);
+    CudaTensor forward_qwen2(const std::vector<int64_t>& tokens, int64_t pos, int slot);
+    CudaTensor forward_gemma(const std::vector<int64_t>& tokens, int64_t pos, int slot);
     CudaTensor logits_tensor(CudaTensor x, int64_t n_batch);
     void greedy_step(const int64_t* token, int64_t pos, int64_t hist_index, float* logits_async);
     CudaTensor forward_multi_query_attention(CudaTensor q, CudaTensor k, CudaTensor v, int l, int64_t n_batch);
-    CudaTensor forward_ffn(CudaTensor x, int l);
+    CudaTensor forward_ffn(CudaTensor x, int l, bool gelu = false);
     void forward(const std::vector<int64_t>& tokens, int64_t pos, float* logits_out);
 };
 
@@ -59,7 +62,7 @@ CudaTensor ccr_runner::logits_tensor(CudaTensor x, int64_t n_batch) {
 
 // llama2.rs:184-211
 void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float* logits_out) {
-    CudaTensor lg = logits_tensor(forward_llama(tokens, pos), (int64_t)tokens.size());
+    CudaTensor lg = logits_tensor(forward_arch(tokens, pos), (int64_t)tokens.size());
     if (logits_out) lg.export_to(logits_out, (size_t)conf.vocab_size);
     else CudaTensor::check(dev, cc_device_flush(dev));     // lazy mode: submit this token's work without a host sync
 }
@@ -67,7 +70,7 @@ void ccr_runner::forward(const std::vector<int64_t>& tokens, int64_t pos, float*
 // One decode step whose sampled token never visits the host: forward (token from the host, or -- token == nullptr -- from device slot 0),
 // greedy argmax (sampler.rs:109-116) into slot 0 and the device-side history; optionally the logits are exported WITHOUT waiting.
 void ccr_runner::greedy_step(const int64_t* token, int64_t pos, int64_t hist_index, float* logits_async) {
-    CudaTensor x = token ? forward_llama({*token}, pos) : forward_llama({0}, pos, 0);
+    CudaTensor x = token ? forward_arch({*token}, pos) : forward_arch({0}, pos, 0);
     CudaTensor lg = logits_tensor(std::move(x), 1);
     lg.argmax_to_slot(0, hist_index);
     if (logits_async) lg.export_async(logits_async, (size_t)conf.vocab_size);     // flushes (asynchronously) as well
@@ -113,6 +116,94 @@ CudaTensor ccr_runner::forward_llama(const std::vector<int64_t>& tokens, int64_t
     return std::move(x).with_name("final_rmsnorm:" + std::to_string(pos));
 }
 
+// llama2.rs:186-192: dispatch on the model architecture
+CudaTensor ccr_runner::forward_arch(const std::vector<int64_t>& tokens, int64_t pos, int slot) {
+    switch (conf.arch) {
+    case CCR_ARCH_QWEN2: return forward_qwen2(tokens, pos, slot);
+    case CCR_ARCH_GEMMA: return forward_gemma(tokens, pos, slot);
+    default: return forward_llama(tokens, pos, slot);
+    }
+}
+
+// llama2.rs:283-352
+CudaTensor ccr_runner::forward_qwen2(const std::vector<int64_t>& tokens, int64_t pos, int slot) {
+    const int64_t embed_dim = conf.embedding_dim, n_heads = local_heads(), n_kv_heads = local_kv_heads();
+    const int64_t head_dim = head_size();
+    const int64_t rope_dim = conf.rope_dim > 0 ? conf.rope_dim : head_dim;
+    const int64_t n_batch = (int64_t)tokens.size();
+
+    CudaTensor x = CudaTensor::alloc({n_batch, embed_dim}, CC_F32, dev);
+    if (slot >= 0) x.copy_rows_from_slot(token_embed, slot);
+    else x.copy_rows_from(token_embed, tokens);
+
+    for (int l = 0; l < conf.n_layers; l++) {
+        CudaTensor x_attn_orig = x.dup();
+        x = std::move(x).rms_norm_inplace(conf.rms_norm_eps);
+        x = std::move(x).mul_inplace(rms_att[l]);
+        x = std::move(x).with_name("attn_rmsnorm:" + std::to_string(l) + ":" + std::to_string(pos));
+
+        CudaTensor q = wq[l].matmul_vec(x);
+        CudaTensor k = wk[l].matmul_vec(x);
+        CudaTensor v = wv[l].matmul_vec(x);
+        q = std::move(q).add_inplace(bq[l]);
+        k = std::move(k).add_inplace(bk[l]);
+        v = std::move(v).add_inplace(bv[l]);
+
+        q = std::move(q).reshape({n_batch, n_heads, head_dim});
+        k = std::move(k).reshape({n_batch, n_kv_heads, head_dim});
+        q = std::move(q).rope_inplace(CC_ROPE_NEOX, pos, rope_dim);
+        k = std::move(k).rope_inplace(CC_ROPE_NEOX, pos, rope_dim);
+
+        x = forward_multi_query_attention(std::move(q), std::move(k), std::move(v), l, n_batch);
+        x = std::move(x).with_name("attn_out:" + std::to_string(l) + ":" + std::to_string(pos));
+        x = std::move(x).add_inplace(x_attn_orig);
+        x = forward_ffn(std::move(x), l, false);
+        x = std::move(x).with_name("ffn_out:" + std::to_string(l) + ":" + std::to_string(pos));
+    }
+    x = std::move(x).rms_norm_inplace(conf.rms_norm_eps);
+    x = std::move(x).mul_inplace(rms_final);
+    return std::move(x).with_name("final_rmsnorm:" + std::to_string(pos));
+}
+
+// llama2.rs:455-524
+CudaTensor ccr_runner::forward_gemma(const std::vector<int64_t>& tokens, int64_t pos, int slot) {
+    const int64_t embed_dim = conf.embedding_dim, n_heads = local_heads(), n_kv_heads = local_kv_heads();
+    const int64_t head_dim = head_size();
+    const int64_t rope_dim = conf.rope_dim > 0 ? conf.rope_dim : head_dim;
+    const int64_t n_batch = (int64_t)tokens.size();
+
+    CudaTensor x = CudaTensor::alloc({n_batch, embed_dim}, CC_F32, dev);
+    if (slot >= 0) x.copy_rows_from_slot(token_embed, slot);
+    else x.copy_rows_from(token_embed, tokens);
+    // GEMMA: the embedding is scaled by sqrt(embed_dim)
+    x = std::move(x).scale_inplace(std::sqrt((float)embed_dim));
+    x = std::move(x).with_name("scaled_embed");
+
+    for (int l = 0; l < conf.n_layers; l++) {
+        CudaTensor x_attn_orig = x.dup();
+        x = std::move(x).rms_norm_inplace(conf.rms_norm_eps);
+        x = std::move(x).mul_inplace(rms_att[l]);
+        x = std::move(x).with_name("attn_rmsnorm:" + std::to_string(l) + ":" + std::to_string(pos));
+
+        CudaTensor q = wq[l].matmul_vec(x);
+        CudaTensor k = wk[l].matmul_vec(x);
+        CudaTensor v = wv[l].matmul_vec(x);
+
+        q = std::move(q).reshape({n_heads, head_dim});
+        k = std::move(k).reshape({n_kv_heads, head_dim});
+        q = std::move(q).rope_inplace(CC_ROPE_NEOX, pos, rope_dim);
+        k = std::move(k).rope_inplace(CC_ROPE_NEOX, pos, rope_dim);
+
+        x = forward_multi_query_attention(std::move(q), std::move(k), std::move(v), l, n_batch);
+        x = std::move(x).add_inplace(x_attn_orig);
+        x = forward_ffn(std::move(x), l, true);
+        x = std::move(x).with_name("ffn_out:" + std::to_string(l) + ":" + std::to_string(pos));
+    }
+    x = std::move(x).rms_norm_inplace(conf.rms_norm_eps);
+    x = std::move(x).mul_inplace(rms_final);
+    return std::move(x).with_name("final_rmsnorm:" + std::to_string(pos));
+}
+
 // llama2.rs:527-603
 CudaTensor ccr_runner::forward_multi_query_attention(CudaTensor q, CudaTensor k, CudaTensor v, int l, int64_t n_batch) {
     const int64_t n_heads = local_heads(), n_kv_heads = local_kv_heads(), head_dim = head_size(), embed_dim = n_heads * head_dim;
@@ -141,13 +232,13 @@ CudaTensor ccr_runner::forward_multi_query_attention(CudaTensor q, CudaTensor k,
 }
 
 // llama2.rs:605-638
-CudaTensor ccr_runner::forward_ffn(CudaTensor x, int l) {
+CudaTensor ccr_runner::forward_ffn(CudaTensor x, int l, bool gelu) {
     CudaTensor x_orig_ffn = x.dup();
     x = std::move(x).rms_norm_inplace(1e-5f);              // literal in the reference (quirk B5)
     x = std::move(x).mul_inplace(rms_ffn[l]);
     CudaTensor h1 = ffn_gate[l].matmul_vec(x);
     CudaTensor h2 = ffn_up[l].matmul_vec(x);
-    h1 = std::move(h1).silu_inplace();
+    h1 = gelu ? std::move(h1).gelu_inplace() : std::move(h1).silu_inplace();      // Activation::{SiLU, GeLU} (llama2.rs:624-628)
     h1 = std::move(h1).mul_inplace(h2);
     x = ffn_down[l].matmul_vec(h1);
     if (world() > 1) x = std::move(x).all_reduce_sum_inplace();          // column-split ffn_down
@@ -187,6 +278,8 @@ extern "C" CC_API int ccr_runner_create(cc_device* dev, const ccr_llama_config* 
         const int64_t dim = conf->embedding_dim, hd = dim / conf->n_heads;
         const int64_t q_dim = hd * r->local_heads(), kv_dim = hd * r->local_kv_heads();
         const int64_t hidden = N > 1 ? conf->hidden_local : conf->hidden_dim, vocab_rows = conf->vocab_size / N;
+        if (conf->arch < CCR_ARCH_LLAMA || conf->arch > CCR_ARCH_GEMMA) throw crabml::TensorError("unknown architecture id");
+        if (N > 1 && conf->arch != CCR_ARCH_LLAMA) throw crabml::TensorError("sharding: only the llama forward is sharded");
         if (N > 1) {
             if (conf->n_heads % N || conf->n_kv_heads % N || conf->vocab_size % N) throw crabml::TensorError("sharding: heads / kv heads / vocab must divide by the world size");
             // the F32-cache attention of the reference pairs query head h with kv head h % n_kv (batch_matmul.rs:47-71, quirk B13):
@@ -206,6 +299,12 @@ extern "C" CC_API int ccr_runner_create(cc_device* dev, const ccr_llama_config* 
             r->ffn_gate.push_back(CudaTensor::wrap(dev, w->ffn_gate[l], {hidden, dim}));
             r->ffn_down.push_back(CudaTensor::wrap(dev, w->ffn_down[l], {dim, hidden}));
             r->ffn_up.push_back(CudaTensor::wrap(dev, w->ffn_up[l], {hidden, dim}));
+            if (conf->arch == CCR_ARCH_QWEN2) {
+                if (!w->bq || !w->bk || !w->bv) throw crabml::TensorError("qwen2: the q/k/v biases are missing");
+                r->bq.push_back(CudaTensor::wrap(dev, w->bq[l], {q_dim}));
+                r->bk.push_back(CudaTensor::wrap(dev, w->bk[l], {kv_dim}));
+                r->bv.push_back(CudaTensor::wrap(dev, w->bv[l], {kv_dim}));
+            }
             r->rms_att.push_back(CudaTensor::wrap(dev, w->rms_att[l], {dim}));
             r->rms_ffn.push_back(CudaTensor::wrap(dev, w->rms_ffn[l], {dim}));
             // llama2.rs:65-86: pre-allocated [n_kv_heads, seq_len, head_dim], resized to length 0

@@ -24,6 +24,7 @@ class LlamaConfig:                      # crabml-llama2/src/model.rs:30-53
     vocab_size: int
     rms_norm_eps: float = 1e-5
     rope_dim: int = 0
+    arch: str = "llama"                 # ModelArchitecture (model.rs:21-27): "llama" | "qwen2" | "gemma"
 
     def head_size(self):
         return self.embedding_dim // self.n_heads
@@ -52,7 +53,8 @@ class LlamaRunner:
         L = conf.n_layers
         cconf = capi.ccr_llama_config(conf.n_heads, conf.n_kv_heads, L, conf.embedding_dim, conf.hidden_dim, conf.seq_len,
                                       conf.vocab_size, conf.rope_dim or 0, conf.rms_norm_eps, int(f16_kv),
-                                      plan.rank if plan else 0, plan.world if plan else 1, plan.hidden_local if plan else conf.hidden_dim)
+                                      plan.rank if plan else 0, plan.world if plan else 1, plan.hidden_local if plan else conf.hidden_dim,
+                                      {"llama": 0, "qwen2": 1, "gemma": 2}[conf.arch])
 
         def arr(key):
             a = (C.c_void_p * L)(*[t.buf.handle.value for t in weights[key]])
@@ -61,7 +63,8 @@ class LlamaRunner:
         self._keep = []
         cw = capi.ccr_llama_weights(weights["token_embed"].buf.handle, arr("wq"), arr("wk"), arr("wv"), arr("wo"), arr("ffn_gate"),
                                     arr("ffn_down"), arr("ffn_up"), arr("rms_att"), arr("rms_ffn"), weights["rms_final"].buf.handle,
-                                    weights["output_weight"].buf.handle if weights.get("output_weight") is not None else None)
+                                    weights["output_weight"].buf.handle if weights.get("output_weight") is not None else None,
+                                    arr("bq") if "bq" in weights else None, arr("bk") if "bk" in weights else None, arr("bv") if "bv" in weights else None)
         h = C.c_void_p()
         rc = device.lib.ccr_runner_create(device.handle, C.byref(cconf), C.byref(cw), kv_seq_len, C.byref(h))
         if rc != capi.CC_OK:

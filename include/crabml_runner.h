@@ -25,7 +25,13 @@ typedef struct ccr_llama_config {
     /* sharded decode (not in the reference: SURVEY 8e).  shard_world <= 1: single device.  Otherwise the weights passed to
      * ccr_runner_create are THIS rank's shards (crabml_b200/sharding.py) and hidden_local is its share of hidden_dim. */
     int32_t shard_rank, shard_world, hidden_local;
+    /* ModelArchitecture (model.rs:21-27): which forward replays -- 0 llama (llama2.rs:213-281), 1 qwen2 (:283-352: q/k/v bias adds, Neox
+     * RoPE), 2 gemma (:455-524: embedding scaled by sqrt(dim), Neox RoPE, GeLU ffn, tied classifier) */
+    int32_t arch;
 } ccr_llama_config;
+#define CCR_ARCH_LLAMA 0
+#define CCR_ARCH_QWEN2 1
+#define CCR_ARCH_GEMMA 2
 
 /* LlamaWeights<T>, model.rs:55-84; arrays have n_layers entries; output_weight may be NULL (llama2.rs:201-206) */
 typedef struct ccr_llama_weights {
@@ -35,6 +41,7 @@ typedef struct ccr_llama_weights {
     cc_buf* const* rms_att; cc_buf* const* rms_ffn;
     cc_buf* rms_final;
     cc_buf* output_weight;
+    cc_buf* const* bq; cc_buf* const* bk; cc_buf* const* bv;      /* qwen2 only (model.rs bq/bk/bv), else NULL */
 } ccr_llama_weights;
 
 typedef struct ccr_runner ccr_runner;

@@ -29,6 +29,7 @@ class LlamaConfig:                       # model.rs:30-53
     vocab_size: int
     rms_norm_eps: float
     rope_dim: int | None
+    arch: str = "llama"                  # ModelArchitecture, model.rs:21-27: "llama" | "qwen2" | "gemma"
 
     def head_size(self):
         return self.embedding_dim // self.n_heads
@@ -48,6 +49,9 @@ class LlamaWeights:                      # model.rs:55-84 (llama subset)
     rms_ffn_weight: list
     rms_final_weight: object
     output_weight: object | None
+    bq: list | None = None               # qwen2 (model.rs bq / bk / bv)
+    bk: list | None = None
+    bv: list | None = None
 
 
 class GGUFModel:
@@ -211,7 +215,7 @@ class Llama2Runner:
 
     def forward(self, tokens, pos):      # llama2.rs:184-211
         T = self.T
-        x = self.forward_llama(tokens, pos)
+        x = {"llama": self.forward_llama, "qwen2": self.forward_qwen2, "gemma": self.forward_gemma}[self.conf.arch](tokens, pos)   # llama2.rs:186-192
         x_final = T.alloc([self.conf.embedding_dim], F32, self.device)
         x_final.copy_rows_from(x, [len(tokens) - 1])
         output_weight = self.weights.output_weight if self.weights.output_weight is not None else self.weights.token_embed
@@ -259,6 +263,66 @@ class Llama2Runner:
         x = x.mul_inplace(w.rms_final_weight)
         return x.with_name(f"final_rmsnorm:{pos}")
 
+    def forward_qwen2(self, tokens, pos):        # llama2.rs:283-352
+        T, conf, w = self.T, self.conf, self.weights
+        embed_dim, n_heads, n_kv_heads, head_dim = conf.embedding_dim, conf.n_heads, conf.n_kv_heads, conf.head_size()
+        rope_dim = conf.rope_dim if conf.rope_dim is not None else head_dim
+        n_batch = len(tokens)
+        x = T.alloc([n_batch, embed_dim], F32, self.device)
+        x.copy_rows_from(w.token_embed, tokens)
+        for l in range(conf.n_layers):
+            x_attn_orig = x.dup()
+            x = x.rms_norm_inplace(conf.rms_norm_eps)
+            x = x.mul_inplace(w.rms_att_weight[l])
+            x = x.with_name(f"attn_rmsnorm:{l}:{pos}")
+            q = w.wq[l].matmul_vec(x)
+            k = w.wk[l].matmul_vec(x)
+            v = w.wv[l].matmul_vec(x)
+            q = q.add_inplace(w.bq[l])
+            k = k.add_inplace(w.bk[l])
+            v = v.add_inplace(w.bv[l])
+            q = q.reshape([n_batch, n_heads, head_dim])
+            k = k.reshape([n_batch, n_kv_heads, head_dim])
+            q = q.rope_inplace(ROPE_NEOX, pos, rope_dim)
+            k = k.rope_inplace(ROPE_NEOX, pos, rope_dim)
+            x = self.forward_multi_query_attention(q, k, v, l, pos, n_kv_heads, n_heads, embed_dim, head_dim, n_batch)
+            x = x.with_name(f"attn_out:{l}:{pos}")
+            x = x.add_inplace(x_attn_orig)
+            x = self.forward_ffn(x, l, pos)
+            x = x.with_name(f"ffn_out:{l}:{pos}")
+        x = x.rms_norm_inplace(conf.rms_norm_eps)
+        x = x.mul_inplace(w.rms_final_weight)
+        return x.with_name(f"final_rmsnorm:{pos}")
+
+    def forward_gemma(self, tokens, pos):        # llama2.rs:455-524
+        T, conf, w = self.T, self.conf, self.weights
+        embed_dim, n_heads, n_kv_heads, head_dim = conf.embedding_dim, conf.n_heads, conf.n_kv_heads, conf.head_size()
+        rope_dim = conf.rope_dim if conf.rope_dim is not None else head_dim
+        n_batch = len(tokens)
+        x = T.alloc([n_batch, embed_dim], F32, self.device)
+        x.copy_rows_from(w.token_embed, tokens)
+        x = x.scale_inplace(float(np.sqrt(np.float32(embed_dim))))      # (embed_dim as f32).sqrt()
+        x = x.with_name("scaled_embed")
+        for l in range(conf.n_layers):
+            x_attn_orig = x.dup()
+            x = x.rms_norm_inplace(conf.rms_norm_eps)
+            x = x.mul_inplace(w.rms_att_weight[l])
+            x = x.with_name(f"attn_rmsnorm:{l}:{pos}")
+            q = w.wq[l].matmul_vec(x)
+            k = w.wk[l].matmul_vec(x)
+            v = w.wv[l].matmul_vec(x)
+            q = q.reshape([n_heads, head_dim])
+            k = k.reshape([n_kv_heads, head_dim])
+            q = q.rope_inplace(ROPE_NEOX, pos, rope_dim)
+            k = k.rope_inplace(ROPE_NEOX, pos, rope_dim)
+            x = self.forward_multi_query_attention(q, k, v, l, pos, n_kv_heads, n_heads, embed_dim, head_dim, n_batch)
+            x = x.add_inplace(x_attn_orig)
+            x = self.forward_ffn(x, l, pos, gelu=True)
+            x = x.with_name(f"ffn_out:{l}:{pos}")
+        x = x.rms_norm_inplace(conf.rms_norm_eps)
+        x = x.mul_inplace(w.rms_final_weight)
+        return x.with_name(f"final_rmsnorm:{pos}")
+
     def forward_multi_query_attention(self, q, k, v, l, pos, n_kv_heads, n_heads, embed_dim, head_dim, n_batch):
         # llama2.rs:527-603
         k = k.reshape([n_batch, n_kv_heads, head_dim]).transpose([1, 0, 2])
@@ -286,14 +350,14 @@ class Llama2Runner:
         self.value_cache[l] = v_cache.with_strider(v_strider_orig)
         return self.weights.wo[l].matmul_vec(x_with_attn)
 
-    def forward_ffn(self, x, l, pos):    # llama2.rs:605-638
+    def forward_ffn(self, x, l, pos, gelu=False):    # llama2.rs:605-638 (Activation::SiLU | GeLU)
         w = self.weights
         x_orig_ffn = x.dup()
         x = x.rms_norm_inplace(1e-5)     # literal, llama2.rs:611 (B5)
         x = x.mul_inplace(w.rms_ffn_weight[l])
         h1 = w.ffn_gate_weight[l].matmul_vec(x)
         h2 = w.ffn_up_weight[l].matmul_vec(x)
-        h1 = h1.silu_inplace()
+        h1 = h1.gelu_inplace() if gelu else h1.silu_inplace()
         h1 = h1.mul_inplace(h2)
         x = w.ffn_down_weight[l].matmul_vec(h1)
         if self.world > 1:

@@ -82,6 +82,7 @@ class TraceTensor:
     def rms_norm_inplace(self, eps): self.log(f"rms_norm {self.V()} eps={_f(eps)}"); return self
     def softmax_inplace(self, axis): self.log(f"softmax {self.V()} axis={axis}"); return self
     def silu_inplace(self): self.log(f"silu {self.V()}"); return self
+    def gelu_inplace(self): self.log(f"gelu {self.V()}"); return self
     def mul_inplace(self, r): self.log(f"mul {self.V()} rhs={r.V()}"); return self
     def add_inplace(self, r): self.log(f"add {self.V()} rhs={r.V()}"); return self
     def scale_inplace(self, f): self.log(f"scale {self.V()} f={_f(f)}"); return self
@@ -238,3 +239,60 @@ def test_cpp_runner_greedy_loop_keeps_the_reference_forward_and_samples_on_the_d
     assert [ln for ln in got if ln.startswith("argmax_to_slot")] == [f"argmax_to_slot [32000]/[1]:0 slot=0 hist={i}" for i in range(4)]
     assert got[-1] == "read_history first=0 count=4"
     assert sum(1 for ln in got if ln.startswith("copy_rows_from_slot")) == 3
+
+
+@pytest.mark.parametrize("arch", ["qwen2", "gemma"])
+def test_cpp_runner_other_architectures_issue_the_reference_op_sequence(mock_runner, arch):
+    """forward_qwen2 (llama2.rs:283-352: bias adds on q/k/v, Neox RoPE) and forward_gemma (llama2.rs:455-524: embedding scaled by
+    sqrt(dim), 2-d q/k views, Neox RoPE, GeLU ffn, tied classifier): the C++ replay against the Python replay, call for call."""
+    L = mock_runner
+    conf = OConf(8, 4, 2, 256, 512, 64, 1000, 1e-6, 32, arch)
+    dim, nl, hd = conf.embedding_dim, conf.n_layers, 32
+    qd, kvd = hd * conf.n_heads, hd * conf.n_kv_heads
+    wt = oc.Q8_0
+    keep = []
+
+    def arr(dtype, n):
+        a = (C.c_void_p * nl)(*[L.mock_new_buf(dtype, n) for _ in range(nl)])
+        keep.append(a)
+        return C.cast(a, C.POINTER(C.c_void_p))
+    tied = arch == "gemma"
+    w = capi.ccr_llama_weights(L.mock_new_buf(wt, conf.vocab_size * dim), arr(wt, qd * dim), arr(wt, kvd * dim), arr(wt, kvd * dim), arr(wt, dim * qd),
+                               arr(wt, 512 * dim), arr(wt, dim * 512), arr(wt, 512 * dim), arr(oc.F32, dim), arr(oc.F32, dim), L.mock_new_buf(oc.F32, dim),
+                               None if tied else L.mock_new_buf(wt, conf.vocab_size * dim),
+                               arr(oc.F32, qd) if arch == "qwen2" else None, arr(oc.F32, kvd) if arch == "qwen2" else None, arr(oc.F32, kvd) if arch == "qwen2" else None)
+    cconf = capi.ccr_llama_config(8, 4, nl, dim, 512, 64, 1000, 32, 1e-6, 0, 0, 1, 512, {"qwen2": 1, "gemma": 2}[arch])
+    h = C.c_void_p()
+    L.mock_trace_clear()
+    assert L.ccr_runner_create(L.mock_device(), C.byref(cconf), C.byref(w), 16, C.byref(h)) == 0, L.ccr_runner_last_error(h)
+    logits = np.zeros(conf.vocab_size, np.float32)
+    steps = [(0, 1), (1, 365)]
+    for pos, tok in steps:
+        t = (C.c_int64 * 1)(tok)
+        assert L.ccr_runner_forward(h, t, 1, pos, logits.ctypes.data_as(C.c_void_p)) == 0, L.ccr_runner_last_error(h)
+    buf = C.create_string_buffer(int(L.mock_trace_size()) + 1)
+    L.mock_trace_copy(buf)
+    got = buf.value.decode().splitlines()
+    L.ccr_runner_destroy(h)
+    dev = TraceDevice()
+
+    def W(shape, t): return TraceTensor.weight(shape, t, dev)
+    lw = LlamaWeights(token_embed=W([conf.vocab_size, dim], wt), wq=[W([qd, dim], wt) for _ in range(nl)], wk=[W([kvd, dim], wt) for _ in range(nl)],
+                      wv=[W([kvd, dim], wt) for _ in range(nl)], wo=[W([dim, qd], wt) for _ in range(nl)],
+                      ffn_gate_weight=[W([512, dim], wt) for _ in range(nl)], ffn_down_weight=[W([dim, 512], wt) for _ in range(nl)],
+                      ffn_up_weight=[W([512, dim], wt) for _ in range(nl)], rms_att_weight=[W([dim], oc.F32) for _ in range(nl)],
+                      rms_ffn_weight=[W([dim], oc.F32) for _ in range(nl)], rms_final_weight=W([dim], oc.F32),
+                      output_weight=None if tied else W([conf.vocab_size, dim], wt),
+                      bq=[W([qd], oc.F32) for _ in range(nl)], bk=[W([kvd], oc.F32) for _ in range(nl)], bv=[W([kvd], oc.F32) for _ in range(nl)])
+    r = Llama2Runner(TraceTensor, conf, lw, dev, 16)
+    for pos, tok in steps:
+        r.forward([tok], pos)
+    want = dev.trace
+    assert len(got) == len(want), (len(got), len(want), [(a, b) for a, b in zip(got, want) if a != b][:5])
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, f"{arch} call {i}: C++ runner `{a}` vs reference replay `{b}`"
+    assert any(ln.startswith("rope") and "mode=1" in ln for ln in got)
+    if arch == "gemma":
+        assert any(ln.startswith("gelu") for ln in got) and any(ln.startswith("scale") for ln in got) and any(ln.startswith("tap scaled_embed") for ln in got)
+    else:
+        assert sum(1 for ln in got if ln.startswith("add") and ":0 rhs=[256]" in ln or ln.startswith("add") and "rhs=[128]" in ln) >= 2 * nl
