@@ -529,7 +529,9 @@ struct Fuser {
     // megakernel only: phases[at] = NORMQ (not write-back) directly followed by its single MATVEC consumer -> one MATVEC
     // phase with a fused prologue (saves a grid barrier per merge; see mega.cu phase_matvec)
     void merge_prologue(size_t at) {
-        if (at + 2 != P.phases.size()) return;
+        // [at] NORMQ, [at + 1] MATVEC, optionally [at + 2] the REDUCE / GATHER half of the matvec's exchange (sharded path)
+        const bool tail = at + 3 == P.phases.size() && (P.phases[at + 2].type == MK_REDUCE || P.phases[at + 2].type == MK_GATHER);
+        if (at + 2 != P.phases.size() && !tail) return;
         MkPhase& nq = P.phases[at];
         MkPhase& mv = P.phases[at + 1];
         if (nq.type != MK_NORMQ || mv.type != MK_MATVEC || nq.write_back || nq.n != mv.mv.k) return;

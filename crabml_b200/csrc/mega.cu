@@ -57,8 +57,9 @@ struct MkSpin {
 // xgpu: this CTA stored partial rows into the peers' exchange slots.  Those stores are ordered before the peers' reads by the chain
 // (CTA i) red.release.gpu -> (CTA 0) ld.acquire.gpu ... fence.sys + st.release.sys -> (peer) ld.acquire.sys: release/acquire patterns of
 // different scopes compose (PTX memory model: causality order is transitive over morally strong synchronisation), so a system-scope
-// fence in EVERY CTA is not required; sysfence = true keeps it (it waits for this CTA's NVLink stores to be acknowledged, ~2 us).
-__device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen, bool xgpu = false, bool sysfence = true) {
+// fence in EVERY CTA is not required (default: off; the 2-GPU parity test runs this way); sysfence = true adds it (it waits for this
+// CTA's NVLink stores to be acknowledged, ~2.5 us per exchange).
+__device__ __forceinline__ void grid_barrier_arrive(unsigned* bar, unsigned nblocks, unsigned gen, bool xgpu = false, bool sysfence = false) {
     __syncthreads();
     if (threadIdx.x == MK_BAR_THREAD) {
         if (xgpu && sysfence) __threadfence_system();
@@ -855,7 +856,8 @@ __device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsigned xs
 #define MK_F_LOOK 1
 #define MK_F_WSTAGE 4
 #define MK_F_POLLCNT 8
-#define MK_F_NOSYSFENCE 256    // exchange phases: no system-scope fence in every CTA before the arrival (see grid_barrier_arrive)
+#define MK_F_SYSFENCE 256      // exchange phases: a system-scope fence in EVERY CTA before its arrival (not needed, see grid_barrier_arrive;
+                               // profiles/r02j: 2351 us vs 2265 us per token at N = 2)
 #define MK_F_TESTSTALL 128     // test hook: the last CTA leaves before barrier 2 -> every other CTA must time out, not hang
 #define MK_F_XEARLY 64         // the f32 row of the next fused prologue is requested (cp.async) right after the barrier opens
 #define MK_F_EARLY 32          // a warp requests its first segments of the next MATVEC phase as soon as IT has finished its rows
@@ -966,7 +968,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) mega_kernel(const 
         const bool xg = s_ph.xgpu != 0;
         // test hook (tests/test_gpu_robustness.py): one CTA deserts before the third barrier, as if it had never become resident
         if ((flags & MK_F_TESTSTALL) && p == 2 && blockIdx.x == gridDim.x - 1) return;
-        if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg, !(flags & MK_F_NOSYSFENCE));       // its bar.sync also publishes s_next (written just above)
+        if (more) grid_barrier_arrive(bar, gridDim.x, gen, xg, (flags & MK_F_SYSFENCE) != 0);       // its bar.sync also publishes s_next (written just above)
         if (look) {
             const bool next_stream = s_next[0].wtype == CC_Q8_0 || s_next[0].wtype == CC_Q4_0;
             if (!early && next_stream) MK_TYPE_CALL(s_next[0].wtype, matvec_prefetch<CC_Q8_0>(s_next[0].mv, pipe), matvec_prefetch<CC_Q4_0>(s_next[0].mv, pipe));
