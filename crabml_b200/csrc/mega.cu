@@ -82,7 +82,8 @@ __device__ __forceinline__ void grid_barrier_wait(unsigned* bar, unsigned nblock
             if (xseq) {                                     // kernel-uniform: the whole warp takes this branch together
                 __syncwarp();                               // every local CTA has arrived: all partial rows are in the peers' slots
                 if (lane < comm.world) {                    // one lane per peer: publish and poll in parallel, not rank after rank
-                    __threadfence_system();
+                    // st.release.sys orders everything this warp has observed (lane 31's acquire of the arrival counter, handed over
+                    // by the __syncwarp above) before the flag: no separate system fence
                     cc_st_release_sys(comm.flag[lane] + comm.rank * 32, xseq);
                     const unsigned* f = comm.flag[comm.rank] + lane * 32;
                     MkSpin sp;

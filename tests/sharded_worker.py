@@ -159,7 +159,7 @@ def run_gpu(rank, world, transports, one_gpu=False):
         dist.broadcast(ref, 0)
         if transport == "p2p":
             assert np.array_equal(ref.cpu().numpy().view(np.uint32), got.view(np.uint32)), ("ranks diverged", transport, lazy)
-        if one_gpu and rank == 0:
+        if rank == 0:
             modes_seen.setdefault(transport, []).append(got)
         if lazy:
             st = dev.lazy_stats()
@@ -172,9 +172,29 @@ def run_gpu(rank, world, transports, one_gpu=False):
         r.close(); del w; dev.close()
     if rank == 0:
         for transport, outs in modes_seen.items():          # eager, CUDA-graph and megakernel runs of the sharded model agree bit for bit
+            if transport != "p2p":
+                continue                                         # NCCL picks its own summation order
             for o in outs[1:]:
                 assert np.array_equal(o.view(np.uint32), outs[0].view(np.uint32)), "execution modes of the sharded run differ"
         print("sharded parity vs single GPU (max rel):", results, flush=True)
+    # ---- 3. soak of the exchange fused into the megakernel (flag handshake riding on the grid barrier, no per-CTA system fence): ----------
+    # SOAK tokens x 5 exchanges each against the CUDA-graph mode, whose exchange is a kernel of its own with explicit system fences; a peer
+    # row read before it landed (or a slot reused too early) shows up as a bit difference in the logits of that token on some rank
+    soak = int(os.environ.get("CRABML_SHARDED_SOAK", "0" if one_gpu else "400"))
+    if "p2p" in transports and soak:
+        seqs = {}
+        for lazy in (1, 2):
+            dev = CudaTensorDevice(gpu, lazy=lazy)
+            dev.init_comm(rank, world, exchange, "p2p")
+            w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=11, plan=plan)
+            r = R.LlamaRunner(dev, conf, w, soak + 8, plan=plan)
+            seqs[lazy] = np.stack([r.forward([(p * 7919 + 1) % conf.vocab_size], p).copy() for p in range(soak)])
+            dist.barrier()
+            r.close(); del w; dev.close()
+        bad = np.nonzero((seqs[1].view(np.uint32) != seqs[2].view(np.uint32)).any(axis=1))[0]
+        assert bad.size == 0, ("fused exchange differs from the stand-alone exchange kernel at tokens", bad[:8].tolist(), "rank", rank)
+        if rank == 0:
+            print(f"soak: {soak} tokens, {soak * 5} fused exchanges, bit-identical to the graph mode on every rank", flush=True)
     return 0
 
 

@@ -76,7 +76,7 @@ def test_two_gpus_sharded_llama_matches_single_gpu():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    n = 2
+    n = min(int(os.environ.get("CRABML_TEST_WORLD", "2")), torch.cuda.device_count())
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "sharded_worker.py"), "--mode", "gpu"]
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
