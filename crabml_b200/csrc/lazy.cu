@@ -136,6 +136,8 @@ struct Plan {
     std::vector<MkPhase> phases;     // megakernel form of the same plan (valid while mega_ok)
     bool mega_ok = true;
     size_t mega_smem = 1024, mega_wstage = 0;
+    bool mega_ring = false;          // weights through the shared-memory ring (mega_ring.cu)
+    int ring_slot = 0, ring_at_ch = 64;
     bool mega_generic = false;       // some MATVEC phase is generic (K-quant weights): launch the instantiation that carries that code
     void S(uint64_t v) { sig.push_back(v); }
     void SP(const void* p) { sig.push_back((uint64_t)(uintptr_t)p); }
@@ -664,9 +666,23 @@ int cc_lazy_flush(cc_device* dev) {
                     P.phases[t].next_matvec = nxt; P.phases[t].next_matvec2 = nxt2;
                     if (P.phases[t].type == MK_MATVEC) { nxt2 = nxt; nxt = t; }
                 }
+                // weights through the shared-memory ring (mega_ring.cu) when every streaming MATVEC phase can be fed by bulk copies
+                bool ring = cc_mega_ring_enabled(), any_stream = false;
                 for (auto& ph : P.phases) {
-                    P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_phase(ph));
-                    if (ph.type == MK_MATVEC && ph.x && ph.norm_w) P.mega_wstage = std::max(P.mega_wstage, (size_t)ph.n * 4);
+                    if (ph.type == MK_MATVEC && ph.act_type != CC_Q8_K) any_stream = true;
+                    if (!cc_mega_ring_phase_ok(ph)) ring = false;
+                }
+                P.mega_ring = ring && any_stream;
+                for (auto& ph : P.phases) {
+                    if (P.mega_ring) {
+                        P.mega_smem = std::max(P.mega_smem, cc_mega_ring_smem_for_phase(ph));
+                        if (ph.type == MK_MATVEC && ph.act_type == CC_Q8_K && ph.x && ph.norm_w) P.mega_wstage = std::max(P.mega_wstage, (size_t)ph.n * 4);
+                        if (ph.type == MK_MATVEC && ph.act_type != CC_Q8_K) P.ring_slot = std::max(P.ring_slot, ph.wtype == CC_Q8_0 ? 4352 : 2304);
+                        if (ph.type == MK_ATTN) P.ring_at_ch = cc_mega_ring_at_ch(ph);
+                    } else {
+                        P.mega_smem = std::max(P.mega_smem, cc_mega_smem_for_phase(ph));
+                        if (ph.type == MK_MATVEC && ph.x && ph.norm_w) P.mega_wstage = std::max(P.mega_wstage, (size_t)ph.n * 4);
+                    }
                 }
                 if (cudaMalloc(&ge.phases_dev, P.phases.size() * sizeof(MkPhase)) != cudaSuccess ||
                     cudaMemcpy(ge.phases_dev, P.phases.data(), P.phases.size() * sizeof(MkPhase), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -676,8 +692,11 @@ int cc_lazy_flush(cc_device* dev) {
             if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: begin capture: %s", cudaGetErrorString(e));
             if (!rc) {
                 if (use_mega && lz->prof_dev && P.phases.size() < 4000) { lz->prof_types.clear(); for (auto& ph : P.phases) lz->prof_types.push_back(ph.type * 16 + (ph.type == MK_MATVEC ? ph.mv.mats.n + 4 * ph.mv.epilogue + 1024 * (ph.mv.k >> 10) : 0)); }
-                rc = use_mega ? cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem, P.mega_wstage,
-                                               P.phases.size() < 4000 ? lz->prof_dev : nullptr, cc_comm_dev(dev), P.mega_generic) : run_steps(lz->dyn_dev);
+                unsigned long long* prof = P.phases.size() < 4000 ? lz->prof_dev : nullptr;
+                if (!use_mega) rc = run_steps(lz->dyn_dev);
+                else if (P.mega_ring) rc = cc_launch_mega_ring(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem, P.mega_wstage, prof, cc_comm_dev(dev),
+                                                               P.mega_generic, P.ring_slot, P.ring_at_ch, cc_mega_flags());
+                else rc = cc_launch_mega(dev, ge.phases_dev, (int)P.phases.size(), lz->dyn_dev, lz->bar_dev, P.mega_smem, P.mega_wstage, prof, cc_comm_dev(dev), P.mega_generic);
                 e = cudaStreamEndCapture(dev->stream, &graph);
                 if (!rc && e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: end capture: %s", cudaGetErrorString(e));
             }
@@ -727,7 +746,7 @@ int cc_check_async_error(cc_device* dev) {
     if (dev->err_dev) cudaMemset(dev->err_dev, 0, 256);
     if (dev->lz && dev->lz->bar_dev) cudaMemset(dev->lz->bar_dev, 0, 4096);
     return cc_fail(dev, CC_ERR_CUDA, "%s timeout (%s): the grid was not co-resident or a peer GPU stopped responding",
-                   code == 3u ? "exchange kernel" : "megakernel barrier", code == 1u ? "grid barrier" : "cross-GPU handshake");
+                   code == 3u ? "exchange kernel" : "megakernel barrier", code == 1u ? "grid barrier" : code == 4u ? "weight ring" : "cross-GPU handshake");
 }
 
 // developer profiling: per-phase start timestamps (ns) of the last megakernel run + phase type codes
