@@ -39,6 +39,7 @@ WORKLOADS = {
 }
 # dram bytes per megakernel launch from the committed ncu --set full capture (profiles/); None until captured
 TRAFFIC = {("llama2-7b-q8_0", 1): 7030865000 + 12124672}     # profiles/r02e_mega_q8_0_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)
+MEGA_NAMES = {1: ("mega_kernel", "mega.cu, weights through registers"), 2: ("mega_ring_kernel", "mega_ring.cu, weights through a TMA-fed shared-memory ring")}
 TYPE_ID = {"Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q8_0": 8, "Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}
 
 
@@ -244,7 +245,7 @@ def quick_decode(workload: str, local_rank: int, K: int, W: int, start_pos: int)
         out = {"workload": f"{workload}-decode-synthetic", "weights": wt_name, "classifier": ct_name, "value": K / (val_ms * 1e-3), "unit": "tok/s",
                "ms_per_step": val_ms / K, "e2e": {"value": K / (e2e_ms * 1e-3), "unit": "tok/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": conf.vocab_size * 4},
                "gpu_launches_device_resident": int(launches), "steps": K, "warmup": W,
-               "roofline": {"bound": "hbm", "kernel": "mega_kernel" if launches == K else "fused kernels (CUDA graph)", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "roofline": {"bound": "hbm", "kernel": MEGA_NAMES.get(dev.mega_variant(), MEGA_NAMES[1])[0] if launches == K else "fused kernels (CUDA graph)", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": bytes_per_token, "frac_of_8TBs_nominal": gbs / 8000.0}}
         runner.close()
         return out
@@ -380,7 +381,8 @@ def run_b200(args, rank, world, local_rank):
         if lazy == 2 and launches_val == K:
             # the dominant kernel IS the step: one mega_kernel launch per token streams every weight byte of this rank once
             mega_gbs = bytes_per_token / (val_ms / K * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "mega_kernel (mega.cu): one persistent launch per decoded token, all matvec/attention/norm phases",
+            mk_name, mk_file = MEGA_NAMES.get(dev.mega_variant(), MEGA_NAMES[1])
+            roofline = {"bound": "hbm", "kernel": f"{mk_name} ({mk_file}): one persistent launch per decoded token, all matvec/attention/norm phases",
                         "achieved": mega_gbs, "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s", "frac": mega_gbs / peaks["hbm_gbs"],
                         "traffic": TRAFFIC.get((args.workload, world)), "traffic_source": "profiles/ (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if TRAFFIC.get((args.workload, world)) else None,
                         "algorithmic_bytes_per_launch": bytes_per_token, "us_per_launch": val_ms / K * 1e3, "frac_of_8TBs_nominal": mega_gbs / 8000.0}

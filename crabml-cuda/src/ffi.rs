@@ -68,6 +68,7 @@ extern "C" {
         cap: c_int,
         n_out: *mut c_int,
     ) -> c_int;
+    pub fn cc_lazy_mega_variant(dev: *mut cc_device) -> c_int;
     pub fn cc_device_launch_count(dev: *mut cc_device) -> u64;
     pub fn cc_device_set_sm_limit(dev: *mut cc_device, n: i32) -> c_int;
     pub fn cc_device_stream(dev: *mut cc_device) -> *mut c_void;

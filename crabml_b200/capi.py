@@ -89,6 +89,7 @@ def load_library(build_if_missing: bool = True):
         "cc_lazy_stats": (i32, [vp, C.POINTER(u64)]),
         "cc_test_mega_barrier_floor": (i32, [vp, i32, C.POINTER(f32)]),
         "cc_lazy_mega_profile": (i32, [vp, C.POINTER(u64), C.POINTER(i32), i32, C.POINTER(i32)]),
+        "cc_lazy_mega_variant": (i32, [vp]),
         "cc_device_stream": (vp, [vp]),
         "cc_tensor_from_cpu": (i32, [vp, vp, sz, C.POINTER(i64), i32, i32, pp]),
         "cc_tensor_alloc": (i32, [vp, C.POINTER(i64), i32, i32, pp]),

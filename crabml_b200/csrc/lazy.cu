@@ -38,7 +38,7 @@ struct LOp {
 // one captured token graph.  The cache key is a 64-bit fold of the launch signature; `sig` is the signature itself and is compared
 // on every hit (a colliding key must re-capture, never replay another plan's baked pointers); `last_use` drives the LRU bound.
 struct GraphEntry { cudaGraphExec_t exec = nullptr; size_t dyn_bytes = 0; uint64_t launches = 0; MkPhase* phases_dev = nullptr;
-                    std::vector<uint64_t> sig; uint64_t last_use = 0; };
+                    std::vector<uint64_t> sig; uint64_t last_use = 0; int mega_variant = 0; };
 #define LZ_MAX_GRAPHS 64                             // cached token graphs per device (a decode loop needs 2-4)
 
 struct LazyState {
@@ -58,6 +58,7 @@ struct LazyState {
     std::unordered_map<uint64_t, GraphEntry> cache;
     uint64_t flushes = 0, graph_hits = 0, captures = 0, uncached = 0, evictions = 0, collisions = 0;
     uint64_t ns_record = 0, ns_fuse = 0, ns_submit = 0, n_ops = 0;      // host-side cost accounting
+    int mega_variant = 0;            // persistent kernel of the last megakernel flush: 1 mega_kernel, 2 mega_ring_kernel
 };
 
 static LView mkview(const cc_view* v) {
@@ -706,6 +707,7 @@ int cc_lazy_flush(cc_device* dev) {
             }
             if (graph) cudaGraphDestroy(graph);
             if (!rc) {
+                ge.mega_variant = use_mega ? (P.mega_ring ? 2 : 1) : 0;
                 ge.dyn_bytes = P.dyn.size();
                 ge.sig = P.sig;
                 ge.launches = dev->launches - l0;
@@ -717,6 +719,7 @@ int cc_lazy_flush(cc_device* dev) {
         }
         if (!rc) {
             it->second.last_use = lz->flushes;
+            if (it->second.mega_variant) lz->mega_variant = it->second.mega_variant;
             cudaError_t e = cudaGraphLaunch(it->second.exec, dev->stream);
             if (e != cudaSuccess) rc = cc_fail(dev, CC_ERR_CUDA, "lazy: graph launch: %s", cudaGetErrorString(e));
             else dev->launches += it->second.launches;
@@ -760,6 +763,8 @@ extern "C" CC_API int cc_lazy_mega_profile(cc_device* dev, unsigned long long* t
     *n_out = n;
     return CC_OK;
 }
+
+extern "C" CC_API int cc_lazy_mega_variant(cc_device* dev) { return dev && dev->lz ? dev->lz->mega_variant : 0; }
 
 extern "C" CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out4) {
     if (!dev || !dev->lz || !out4) return CC_ERR_ARG;

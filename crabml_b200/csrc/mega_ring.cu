@@ -97,6 +97,9 @@ __device__ __forceinline__ int mr_locate(const StreamMats& M, const MrGeo& g, in
 // slot's "full" barrier with the byte count, issues the two bulk copies (quants, scales) and publishes the entry number in the slot's
 // sequence word.  Consumers check that word before they look at the barrier: an mbarrier parity alone cannot tell "this use has not
 // landed" from "the previous use has not landed" when a warp gets more than one lap ahead (16 warps x 3 segments > 40 slots).
+// (Measured, profiles/r02q: 1 / 2 / 4 / 8 producer warps = 2859 / 2782 / 2262 / 2435 us per token -- a warp's probe-and-issue trip takes ~400
+// cycles, so the number of polling warps bounds the refill rate, and at 8 the 80-register cap starts to cost.  Sleeping after a failed probe,
+// SIMT-wide parameter computation, in-order probe loops and fence-free hand-back words changed nothing.)
 __device__ void mr_producer(const MkPhase* __restrict__ phases, int n_phases, const MrRing R, unsigned full0, unsigned done0, unsigned ring0,
                             MkPhase* s_pd, volatile unsigned* s_seq, volatile int* s_abort, int* s_prod_done, unsigned long long* prof_tail, const bool pairs) {
     const int lane = threadIdx.x & 31;
@@ -607,7 +610,11 @@ bool cc_mega_ring_phase_ok(const MkPhase& ph) {
         if (((uintptr_t)ph.mv.mats.qs[t] | (uintptr_t)ph.mv.mats.d[t]) & 15u) return false;
     return true;
 }
-int cc_mega_ring_at_ch(const MkPhase& ph) { return ph.at.kv_f16 ? 64 : 32; }       // 48 KB of cache rows in flight per head either way
+int cc_mega_ring_at_ch(const MkPhase& ph) {       // 48 KB of cache rows in flight per head either way (CRABML_RING_ATCH: developer A/B)
+    static const int env = getenv("CRABML_RING_ATCH") ? atoi(getenv("CRABML_RING_ATCH")) : 0;
+    if (env >= 8 && env <= 64) return env;
+    return ph.at.kv_f16 ? 64 : 32;
+}
 size_t cc_mega_ring_smem_for_phase(const MkPhase& ph) {
     if (ph.type == MK_MATVEC && ph.act_type == CC_Q8_K) return cc_mega_smem_for_phase(ph);
     if (ph.type == MK_MATVEC) {

@@ -92,6 +92,9 @@ CC_API int cc_lazy_stats(cc_device* dev, uint64_t* out8);
 CC_API int cc_test_mega_barrier_floor(cc_device* dev, int n, float* us_per_phase);
 /* developer profiling (CRABML_MEGA_PROF=1): phase start timestamps of the last megakernel run */
 CC_API int cc_lazy_mega_profile(cc_device* dev, unsigned long long* ts, int* types, int cap, int* n_out);
+/* which persistent kernel ran the last megakernel flush: 0 none yet, 1 mega_kernel (weights through registers, mega.cu),
+ * 2 mega_ring_kernel (weights through the TMA-fed shared-memory ring, mega_ring.cu) */
+CC_API int cc_lazy_mega_variant(cc_device* dev);
 /* counters: kernels launched by this library since creation (bench.py "gpu_launches") */
 CC_API uint64_t cc_device_launch_count(cc_device* dev);
 /* persistent kernels of this device use at most n SMs (test / co-tenancy hook: two devices of one process side by side on one GPU) */
