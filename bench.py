@@ -38,7 +38,7 @@ WORKLOADS = {
     "llama2-7b-q8_0-prefill": ("LLAMA2_7B", "Q8_0", "Q8_0"),
 }
 # dram bytes per megakernel launch from the committed ncu --set full capture (profiles/); None until captured
-TRAFFIC = {("llama2-7b-q8_0", 1): 7030865000 + 12124672}     # profiles/r02e_mega_q8_0_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)
+TRAFFIC = {("llama2-7b-q8_0", 1): 7040893000 + 49879296}     # profiles/r02p_mega_ring_q8_0_ncu_raw.csv (mega_ring_kernel: dram__bytes_read.sum + dram__bytes_write.sum)
 MEGA_NAMES = {1: ("mega_kernel", "mega.cu, weights through registers"), 2: ("mega_ring_kernel", "mega_ring.cu, weights through a TMA-fed shared-memory ring")}
 TYPE_ID = {"Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q8_0": 8, "Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14}
 
