@@ -280,8 +280,25 @@ __device__ __forceinline__ MkRowPtr mk_vrow_ptr(const StreamMats& M, const MkGeo
 // the same bits) and the weights are not pipelined through registers across phase boundaries.
 // shared memory: qs [k] | d [k/256] | bsums [k/16] (TKBase) | reduction scratch | f32 x
 __device__ __forceinline__ int mk_generic_sx_offset(int k) { return ((TKBase::smem_bytes(k) + 15) & ~15) + 256; }
+// __noinline__ (ring kernel): the K-quant row dots are register-hungry; as a called function they get their own allocation instead of pushing spills into
+// the streaming phases of the same kernel (profiles/r02s: every phase of the Q4_0 body was 15-25 % slower in the instantiation that carries
+// the generic code inline: 2335 vs 1938 us per token for a Q6_K classifier that itself costs 50 us more).
+// MK_GENERIC_NOINLINE (mega_ring.cu): as a called function with registers of its own.  In mega.cu the phase stays inline and borrows the
+// weight pipe's registers: there the pipe would have to be saved around every call.
+#ifndef MK_GENERIC_NOINLINE
+#define MK_GENERIC_NOINLINE 0
+#endif
+#if MK_GENERIC_NOINLINE
+#define MK_GENERIC_ATTR __noinline__
+#define MK_GENERIC_PIPE_PARAM
+#define MK_GENERIC_PIPE_ARG
+#else
+#define MK_GENERIC_ATTR
+#define MK_GENERIC_PIPE_PARAM MkPipe& P,
+#define MK_GENERIC_PIPE_ARG pipe,
+#endif
 template <class T>
-static __device__ void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, bool x_staged, const uint16_t* exp_lut, MkPipe& P, unsigned long long* stamp1) {
+static __device__ MK_GENERIC_ATTR void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, float* s_w, bool w_staged, bool x_staged, const uint16_t* exp_lut, MK_GENERIC_PIPE_PARAM unsigned long long* stamp1) {
     const StreamArgs& A = ph.mv;
     const StreamMats& M = A.mats;
     const int k = A.k;
@@ -377,8 +394,12 @@ static __device__ void phase_matvec_generic(const MkPhase& ph, uint8_t* smem, fl
         // segments = 16-24 LDG.128 per lane in flight), across row boundaries
         const int NSEG = ((k >> 8) + 15) >> 4;
         const int U = n_vrows * NSEG;
+#if MK_GENERIC_NOINLINE
+        KSeg S0, S1;
+#else
         KSeg& S0 = P.buf0;                                                   // the weight pipe's registers (no streaming look-ahead is pending: caller)
         KSeg& S1 = P.buf1;
+#endif
         int x0[4] = {0, 0, 0, 0}, x1[4] = {0, 0, 0, 0};
         int l_i = 0, l_seg = 0;
         auto load = [&](KSeg& S, int (&x)[4], bool valid) {

@@ -18,6 +18,7 @@
 // The 512 compute threads synchronise on named barrier 1 (MK_SYNC); the producer warp never joins it.
 // 20 warps: five per SM sub-partition, so its 16384 registers allow 96 per thread (what __launch_bounds__(640, 1) yields).
 #define MK_SYNC() asm volatile("bar.sync 1, 512;" ::: "memory")
+#define MK_GENERIC_NOINLINE 1
 #include "mega_phases.cuh"
 
 #define MR_PRODUCER_WARPS 4        // 20 warps: five per SM sub-partition, still 96 registers per thread
@@ -532,7 +533,6 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mega_ring_kernel(const MkPhase*
     RC.pairs = (flags & MK_F_RPAIR) != 0; RC.s_unit = &s_unit; RC.s_seq = s_seq; RC.s_dead = &s_ring_dead; RC.err_dev = &bar[MK_BAR_ERR]; RC.err_host = err_host;
     uint8_t* work = smem;
     float* s_w = (float*)(smem + wtop_off);  // generic phases: staging of the norm weights
-    MkPipe pipe;                             // generic (K-quant) phases borrow these registers; nothing lives across phases
     unsigned gen = 0;
     if (threadIdx.x == MK_BAR_THREAD) gen = ld_acquire_u32(&bar[32]);
     unsigned xseq = comm.world > 0 ? *comm.seq : 0u;
@@ -551,12 +551,12 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mega_ring_kernel(const MkPhase*
         case MK_MATVEC:
             if (GEN && s_ph.act_type == CC_Q8_K) {
                 switch (s_ph.wtype) {
-                case CC_Q2_K: phase_matvec_generic<TQ2_K>(s_ph, work, s_w, false, false, exp_lut, pipe, st1); break;
-                case CC_Q3_K: phase_matvec_generic<TQ3_K>(s_ph, work, s_w, false, false, exp_lut, pipe, st1); break;
-                case CC_Q4_K: phase_matvec_generic<TQ45_K<false>>(s_ph, work, s_w, false, false, exp_lut, pipe, st1); break;
-                case CC_Q5_K: phase_matvec_generic<TQ45_K<true>>(s_ph, work, s_w, false, false, exp_lut, pipe, st1); break;
-                case CC_Q6_K: phase_matvec_generic<TQ6_K>(s_ph, work, s_w, false, false, exp_lut, pipe, st1); break;
-                default: phase_matvec_generic<TQ8_K>(s_ph, work, s_w, false, false, exp_lut, pipe, st1); break;
+                case CC_Q2_K: phase_matvec_generic<TQ2_K>(s_ph, work, s_w, false, false, exp_lut, MK_GENERIC_PIPE_ARG st1); break;
+                case CC_Q3_K: phase_matvec_generic<TQ3_K>(s_ph, work, s_w, false, false, exp_lut, MK_GENERIC_PIPE_ARG st1); break;
+                case CC_Q4_K: phase_matvec_generic<TQ45_K<false>>(s_ph, work, s_w, false, false, exp_lut, MK_GENERIC_PIPE_ARG st1); break;
+                case CC_Q5_K: phase_matvec_generic<TQ45_K<true>>(s_ph, work, s_w, false, false, exp_lut, MK_GENERIC_PIPE_ARG st1); break;
+                case CC_Q6_K: phase_matvec_generic<TQ6_K>(s_ph, work, s_w, false, false, exp_lut, MK_GENERIC_PIPE_ARG st1); break;
+                default: phase_matvec_generic<TQ8_K>(s_ph, work, s_w, false, false, exp_lut, MK_GENERIC_PIPE_ARG st1); break;
                 }
                 break;
             }

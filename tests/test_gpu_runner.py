@@ -1,6 +1,8 @@
 """The C++ Llama2Runner replay (crabml_b200/csrc/host/llama2_runner.cpp, the product's host side) end to end:
 golden generations of the reference (llama2.rs:673-703), bit-identical logits in exact_order mode, and a
 Llama-2-7B-SHAPED layer on the synthetic weights bench.py uses (BASELINE.json configs 2-4 at full size)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -175,6 +177,31 @@ def test_lazy_7b_shaped_layer(wt, ct):
     assert np.isfinite(res[0]).all() and np.abs(res[0]).max() > 1e-3
     for mode in (1, 2):
         np.testing.assert_array_equal(res[mode].view(np.uint32), res[0].view(np.uint32), err_msg=f"lazy={mode} vs eager")
+
+
+@pytest.mark.parametrize("wt,ct", [(oc.Q8_0, oc.Q8_0), (oc.Q4_0, oc.Q6_K)])
+def test_both_persistent_kernels_bit_identical_on_7b_shapes(tmp_path, wt, ct):
+    """The two persistent kernels -- weights through registers (mega.cu: what sharded runs and shapes the ring cannot feed use) and
+    weights through the TMA-fed shared-memory ring (mega_ring.cu: the default) -- against the eager kernels on the same 7B-shaped
+    model, each in its own process (the flag word that selects the kernel is read once per process)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = {}
+    for name, lazy, flags in (("eager", 0, None), ("registers", 2, "0x4d"), ("ring", 2, None)):
+        env = dict(os.environ)
+        env.pop("CRABML_MEGA_FLAGS", None)
+        if flags:
+            env["CRABML_MEGA_FLAGS"] = flags
+        out = str(tmp_path / f"{name}.npz")
+        subprocess.run([sys.executable, os.path.join(root, "tests", "mega_variant_worker.py"), str(lazy), str(wt), str(ct), out],
+                       check=True, cwd=root, env=env, timeout=600)
+        got[name] = np.load(out)
+    assert int(got["registers"]["variant"]) == 1 and int(got["ring"]["variant"]) == 2
+    ref = got["eager"]["logits"]
+    assert np.isfinite(ref).all() and np.abs(ref).max() > 1e-3
+    for name in ("registers", "ring"):
+        np.testing.assert_array_equal(got[name]["logits"].view(np.uint32), ref.view(np.uint32), err_msg=f"{name} vs eager")
 
 
 @pytest.mark.parametrize("fname", ["tinyllamas-stories-15m-q8_0.gguf", "tinyllamas-stories-15m-q4_0.gguf"])

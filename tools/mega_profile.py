@@ -11,8 +11,8 @@ from crabml_b200 import CudaTensorDevice, capi  # noqa: E402
 from crabml_b200 import runner as R  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "Q8_0"
-wt = {"Q8_0": capi.Q8_0, "Q4_0": capi.Q4_0, "Q4_K": capi.Q4_K, "Q6_K": capi.Q6_K}[wl]
-ct = capi.Q6_K if wl == "Q4_K" else wt
+wt = {"Q8_0": capi.Q8_0, "Q4_0": capi.Q4_0, "Q4_K": capi.Q4_K, "Q6_K": capi.Q6_K, "Q4_0-Q6K": capi.Q4_0}[wl]      # body type
+ct = capi.Q6_K if wl in ("Q4_K", "Q4_0-Q6K") else wt                                                                # classifier type
 dev = CudaTensorDevice(0, lazy=2)
 conf = R.LLAMA2_7B
 w = R.synthetic_weights(dev, conf, wt, ct)
