@@ -291,6 +291,7 @@ bool cc_mega_ring_enabled();
 bool cc_mega_ring_phase_ok(const MkPhase& ph);
 int cc_mega_ring_at_ch(const MkPhase& ph);
 size_t cc_mega_ring_smem_for_phase(const MkPhase& ph);
+bool cc_mega_ring_fits(size_t smem_work, size_t smem_wstage, int slot_bytes, bool generic);
 int cc_launch_mega_ring(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem_work, size_t smem_wstage,
                         unsigned long long* prof, const CommDev* comm, bool generic, int slot_bytes, int at_ch, int flags);
 int cc_check_async_error(cc_device* dev);     // after a stream synchronize: did a persistent kernel give up on a barrier?

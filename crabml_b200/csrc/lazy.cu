@@ -660,7 +660,15 @@ int cc_lazy_flush(cc_device* dev) {
             uint64_t l0 = dev->launches;
             cudaGraph_t graph = nullptr;
             GraphEntry ge;
-            const bool use_mega = dev->mega && P.mega_ok && !P.phases.empty();
+            bool use_mega = dev->mega && P.mega_ok && !P.phases.empty();
+            if (use_mega) {       // a phase whose working area cannot fit beside anything (e.g. the score row of a 32 K-token context): CUDA-graph mode
+                size_t work = 0, wst = 0;
+                for (auto& ph : P.phases) {
+                    work = std::max(work, cc_mega_smem_for_phase(ph));
+                    if (ph.type == MK_MATVEC && ph.x && ph.norm_w) wst = std::max(wst, (size_t)ph.n * 4);
+                }
+                if (work + wst + 4096 > 227 * 1024) use_mega = false;
+            }
             if (use_mega) {       // phase table lives in device memory for the lifetime of the graph
                 int nxt = -1, nxt2 = -1;
                 for (int t = (int)P.phases.size() - 1; t >= 0; t--) {
@@ -674,6 +682,15 @@ int cc_lazy_flush(cc_device* dev) {
                     if (!cc_mega_ring_phase_ok(ph)) ring = false;
                 }
                 P.mega_ring = ring && any_stream;
+                if (P.mega_ring) {              // is there room for a useful ring beside the working area?  else: the register-pipe kernel
+                    size_t work = 0, wst = 0; int slot = 0;
+                    for (auto& ph : P.phases) {
+                        work = std::max(work, cc_mega_ring_smem_for_phase(ph));
+                        if (ph.type == MK_MATVEC && ph.act_type == CC_Q8_K && ph.x && ph.norm_w) wst = std::max(wst, (size_t)ph.n * 4);
+                        if (ph.type == MK_MATVEC && ph.act_type != CC_Q8_K) slot = std::max(slot, ph.wtype == CC_Q8_0 ? 4352 : 2304);
+                    }
+                    if (!cc_mega_ring_fits(work, wst, slot, P.mega_generic)) P.mega_ring = false;
+                }
                 for (auto& ph : P.phases) {
                     if (P.mega_ring) {
                         P.mega_smem = std::max(P.mega_smem, cc_mega_ring_smem_for_phase(ph));

@@ -624,6 +624,20 @@ size_t cc_mega_ring_smem_for_phase(const MkPhase& ph) {
     if (ph.type == MK_ATTN) return (size_t)(3 * ph.at.hd + ((ph.at.max_len + 8 + 3) & ~3)) * 4 + (size_t)AT_NBUF * cc_mega_ring_at_ch(ph) * ph.at.hd * (ph.at.kv_f16 ? 2 : 4) + 64;
     return 1024;
 }
+// slots the ring would get beside a working area of `smem_work` (+ `smem_wstage`) bytes; lazy.cu falls back to the register-pipe kernel
+// (mega.cu) below MR_MIN_SLOTS -- e.g. a 32 K-token context, whose attention phase needs 128 KB for the score row alone
+#define MR_MIN_SLOTS 12
+static size_t mr_ring_off(size_t smem_work, size_t smem_wstage) { return ((((smem_work + 15) & ~(size_t)15) + smem_wstage) + 127) & ~(size_t)127; }
+int cc_mega_ring_slots(size_t smem_work, size_t smem_wstage, int slot_bytes, bool generic) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, generic ? mega_ring_kernel<true> : mega_ring_kernel<false>) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const size_t cap = 227 * 1024 - fa.sharedSizeBytes, off = mr_ring_off(smem_work, smem_wstage);
+    if (slot_bytes <= 0 || off >= cap) return 0;
+    const size_t n = (cap - off) / (size_t)slot_bytes;
+    return (int)(n > MR_MAX_SLOTS ? MR_MAX_SLOTS : n);
+}
+bool cc_mega_ring_fits(size_t smem_work, size_t smem_wstage, int slot_bytes, bool generic) { return cc_mega_ring_slots(smem_work, smem_wstage, slot_bytes, generic) >= MR_MIN_SLOTS; }
+
 int cc_launch_mega_ring(cc_device* dev, const MkPhase* phases_dev, int n_phases, const uint8_t* dyn_dev, unsigned* bar_dev, size_t smem_work, size_t smem_wstage,
                         unsigned long long* prof, const CommDev* comm, bool generic, int slot_bytes, int at_ch, int flags) {
     auto kern = generic ? mega_ring_kernel<true> : mega_ring_kernel<false>;

@@ -31,11 +31,13 @@ print("CLEAN-EXIT")
 """ % ROOT
 
 
-def test_deserting_cta_is_a_timeout_error_not_a_hang():
+@pytest.mark.parametrize("flags", [0x4D, 0x64D], ids=["register-pipe kernel", "ring kernel"])
+def test_deserting_cta_is_a_timeout_error_not_a_hang(flags):
     """test hook MK_F_TESTSTALL (0x80): the last CTA leaves before the third grid barrier, i.e. the grid behaves as if one CTA had
-    never become resident (another tenant on the GPU).  Every other CTA must give up after the spin bound, the kernel must drain,
-    and the host must see CC_ERR_CUDA 'megakernel barrier timeout' -- within seconds."""
-    env = dict(os.environ, CRABML_MEGA_FLAGS=str(0x4D | 0x80))
+    never become resident (another tenant on the GPU).  Every other CTA must give up after the spin bound, the kernel must drain
+    (ring kernel: the producer warps stop, bulk copies in flight land before the CTA's shared memory goes away), and the host must
+    see CC_ERR_CUDA 'megakernel barrier timeout' -- within seconds."""
+    env = dict(os.environ, CRABML_MEGA_FLAGS=str(flags | 0x80))
     t0 = time.time()
     p = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=120)
     out = p.stdout + p.stderr
@@ -47,3 +49,27 @@ def test_deserting_cta_is_a_timeout_error_not_a_hang():
 def test_same_child_without_the_hook_runs():
     p = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ), capture_output=True, text=True, timeout=120)
     assert "NO-ERROR" in p.stdout and "CLEAN-EXIT" in p.stdout, p.stdout + p.stderr
+
+
+def test_context_too_long_for_the_persistent_kernels_falls_back_to_the_graph_mode():
+    """A 40 K-token KV cache: the attention phase's score row alone (160 KB) leaves no room for its chunk buffers in shared memory, so
+    lazy = 2 must run the token as the CUDA graph of fused kernels instead of failing -- same bits as the eager kernels."""
+    import numpy as np
+    from crabml_b200 import CudaTensorDevice, capi
+    from crabml_b200 import runner as R
+    conf = R.LlamaConfig(32, 32, 1, 4096, 11008, 40000, 32000, 1e-5, 128)
+    res = {}
+    for lazy in (0, 2):
+        dev = CudaTensorDevice(0, lazy=lazy)
+        try:
+            w = R.synthetic_weights(dev, conf, capi.Q8_0, capi.Q8_0, seed=5)
+            r = R.LlamaRunner(dev, conf, w, 40000)
+            res[lazy] = np.stack([r.forward([t], p).copy() for p, t in enumerate([1, 9, 31999])])
+            if lazy:
+                assert dev.mega_variant() == 0, "expected the CUDA-graph fallback"
+                st = dev.lazy_stats()
+                assert st["uncached"] == 0, st
+            r.close()
+        finally:
+            dev.close()
+    np.testing.assert_array_equal(res[2].view(np.uint32), res[0].view(np.uint32))
