@@ -25,9 +25,9 @@
 // fully coalesced LDG.128; total bytes are unchanged (the f16 scales move to their own plane).
 //
 //   type   plane0                         plane1                 plane2            plane3
-//   Q8_0   qs  int8  [rows][k] (*)        d   f16 [rows][k/32]     (*) inside each group of 32 blocks the 16 B
+//   Q8_0   qs  int8  [rows][k] (*)        d   f16 [rows][S]        (*) inside each group of 32 blocks the 16 B
 //                                                                  first halves precede the second halves
-//   Q4_0   qs  u8    [rows][k/32][16]     d   f16 [rows][k/32]
+//   Q4_0   qs  u8    [rows][k/32][16]     d   f16 [rows][S]        S = CC_D_STRIDE(k/32): rows padded to 16 bytes
 //   Q4_1   qs  u8    [rows][k/32][16]     d,m f16x2
 //   Q5_0   qs  u8    [rows][k/32][16]     d   f16                qh u32 [rows][k/32]
 //   Q5_1   qs  u8    [rows][k/32][16]     d,m f16x2              qh u32
@@ -38,6 +38,11 @@
 //   Q6_K   ql  u8    [rows][k/256][128]   qh u8 [..][64]         scales i8 [..][16]   d f16
 //   Q8_K   qs  int8  [rows][k]            d   f32 [rows][k/256]
 // ------------------------------------------------------------------------------------------
+// Q8_0 / Q4_0: the rows of the f16 scale plane are padded to a multiple of 8 blocks (16 bytes), so that any row segment is a legal bulk
+// copy (TMA: 16-byte aligned address, 16-byte multiple size) for every k -- the column-split shards of the sharded path included
+// (k = 11008 / N: 172, 86, 43 blocks per row).  The padding is never read by arithmetic.
+#define CC_D_STRIDE(nb) ((((nb) + 7) / 8) * 8)
+#define CC_HAS_PADDED_D(t) ((t) == CC_Q8_0 || (t) == CC_Q4_0)
 #define CC_MAX_PLANES 4
 #define CC_N_SLOTS 16
 #define CC_HISTORY_CAP 65536

@@ -34,9 +34,9 @@ __device__ inline float dequant_elem(int t, const DeqPlanes& P, int64_t e) {
     switch (t) {
     case CC_Q8_0: {                                                        // buf_q8_0.rs:18-23
         int64_t b = e >> 5;
-        float d = h2f_bits(((const uint16_t*)P.p[1])[b]);
         const int nb = (int)(P.cols >> 5);
         int64_t row = e / P.cols;
+        float d = h2f_bits(((const uint16_t*)P.p[1])[row * CC_D_STRIDE(nb) + (b - row * nb)]);
         int64_t off = row * P.cols + q8_0_row_offset((int)(b - row * nb), (int)(e & 31), nb);
         return (float)((const int8_t*)P.p[0])[off] * d;
     }
@@ -44,7 +44,8 @@ __device__ inline float dequant_elem(int t, const DeqPlanes& P, int64_t e) {
         int64_t b = e >> 5; int i = (int)(e & 31);
         uint8_t q = P.p[0][b * 16 + (i & 15)];
         int x = (i < 16 ? (q & 0x0F) : (q >> 4)) - 8;
-        return (float)x * h2f_bits(((const uint16_t*)P.p[1])[b]);
+        const int64_t nb = P.cols >> 5, row = e / P.cols;
+        return (float)x * h2f_bits(((const uint16_t*)P.p[1])[row * CC_D_STRIDE(nb) + (b - row * nb)]);
     }
     case CC_Q4_1: {                                                        // vec_dot order, buf_q4_1.rs:266-280 (B10)
         int64_t b = e >> 5; int i = (int)(e & 31);

@@ -43,7 +43,7 @@ __device__ __forceinline__ RowPtr row_ptr(const StreamMats& M, int mat, int r, i
     const uint8_t* q0 = mat == 0 ? M.qs[0] : mat == 1 ? M.qs[1] : M.qs[2];
     const uint16_t* d0 = mat == 0 ? M.d[0] : mat == 1 ? M.d[1] : M.d[2];
     p.q = q0 + (size_t)r * nb * BB + lane * 16;
-    p.d = d0 + (size_t)r * nb + lane;
+    p.d = d0 + (size_t)r * CC_D_STRIDE(nb) + lane;
     return p;
 }
 

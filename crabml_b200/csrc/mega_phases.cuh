@@ -270,7 +270,7 @@ __device__ __forceinline__ MkRowPtr mk_vrow_ptr(const StreamMats& M, const MkGeo
     const uint16_t* d0 = mat == 0 ? M.d[0] : mat == 1 ? M.d[1] : M.d[2];
     MkRowPtr p;
     p.q = q0 + (size_t)r * g.nb * BB + lane * 16;
-    p.d = d0 + (size_t)r * g.nb + lane;
+    p.d = d0 + (size_t)r * CC_D_STRIDE(g.nb) + lane;
     return p;
 }
 

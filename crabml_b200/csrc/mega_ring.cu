@@ -143,16 +143,17 @@ __device__ void mr_producer(const MkPhase* __restrict__ phases, int n_phases, co
                     int mat;
                     const int r = mr_locate(M, g, g.first + u * g.stride, v, mat);
                     q0 = M.qs[mat] + ((size_t)r * g.nb + (size_t)sg * (MK_SEG * 32)) * BB;
-                    d0 = M.d[mat] + (size_t)r * g.nb + sg * (MK_SEG * 32);
+                    d0 = M.d[mat] + (size_t)r * CC_D_STRIDE(g.nb) + sg * (MK_SEG * 32);
                     nbe = (unsigned)min(MK_SEG * 32, g.nb - MK_SEG * 32 * sg);
                     e = ent + (unsigned)j; slot = e % (unsigned)R.nslots; use = e / (unsigned)R.nslots;
                     have = true;
                 }
                 if (!use || mr_ld_acquire_shared(done0 + 4u * slot) == e - (unsigned)R.nslots + 1u) {      // the slot's previous tenant has been consumed
                     const unsigned fb = full0 + 8u * slot, dst = ring0 + slot * (unsigned)R.slot_bytes;
-                    mr_expect_tx(fb, nbe * BB + nbe * 2u);
+                    const unsigned dbytes = (nbe * 2u + 15u) & ~15u;        // the scale rows are padded to 16 bytes (CC_D_STRIDE): a short last segment copies its padding
+                    mr_expect_tx(fb, nbe * BB + dbytes);
                     mr_bulk_g2s(dst, q0, nbe * BB, fb);
-                    mr_bulk_g2s(dst + doff, d0, nbe * 2u, fb);
+                    mr_bulk_g2s(dst + doff, d0, dbytes, fb);
                     __threadfence_block();
                     s_seq[slot] = e + 1u;
                     j += 32 * MR_PRODUCER_WARPS; have = false; p_iss++;
@@ -601,11 +602,11 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mega_ring_kernel(const MkPhase*
 
 // ---- host side ---------------------------------------------------------------------------------------------------------------------------
 // a streaming MATVEC phase can be fed by bulk copies when every segment is a whole number of 16-byte units at a 16-byte aligned address
+// (always, since the scale rows are padded: CC_D_STRIDE; the check keeps the pointer alignment honest)
 bool cc_mega_ring_phase_ok(const MkPhase& ph) {
     if (ph.type != MK_MATVEC || ph.act_type == CC_Q8_K) return true;
     if (ph.wtype != CC_Q8_0 && ph.wtype != CC_Q4_0) return false;
-    const int nb = ph.mv.k / 32;
-    if (ph.mv.k % 32 || nb % 8) return false;
+    if (ph.mv.k % 32) return false;
     for (int t = 0; t < ph.mv.mats.n; t++)
         if (((uintptr_t)ph.mv.mats.qs[t] | (uintptr_t)ph.mv.mats.d[t]) & 15u) return false;
     return true;

@@ -35,7 +35,8 @@ size_t cc_device_layout_bytes(int t, int64_t rows, int64_t cols) {
     PlaneSpec ps = plane_spec(t);
     int64_t nblk = rows * (cols / cc_block_elems(t));
     size_t total = 0;
-    for (int p = 0; p < ps.n; p++) total += align256((size_t)nblk * ps.bytes[p]);
+    for (int p = 0; p < ps.n; p++)
+        total += align256(p == 1 && CC_HAS_PADDED_D(t) ? (size_t)rows * CC_D_STRIDE(cols / 32) * 2 : (size_t)nblk * ps.bytes[p]);
     return total ? total : 256;
 }
 
@@ -45,7 +46,7 @@ void cc_assign_planes(cc_buf* b) {
     uint8_t* p = (uint8_t*)b->base;
     for (int i = 0; i < ps.n; i++) {
         b->plane[i] = p;
-        p += align256((size_t)nblk * ps.bytes[i]);
+        p += align256(i == 1 && CC_HAS_PADDED_D(b->dtype) ? (size_t)b->rows * CC_D_STRIDE(b->cols / 32) * 2 : (size_t)nblk * ps.bytes[i]);
     }
 }
 
@@ -56,6 +57,7 @@ struct RepackArgs {
     int n;
     int block_bytes;
     int q8_0_nb;          // > 0: plane 0 is the Q8_0 qs plane with `nb` blocks per row -> half-planar groups
+    int d_nb;             // > 0: plane 1 is a padded f16 scale plane (CC_D_STRIDE) with `nb` blocks per row
 };
 
 template <bool TO_PLANES>
@@ -72,6 +74,10 @@ __global__ void repack_kernel(uint8_t* gguf, RepackArgs a, int64_t nblk, int pla
         int b = (int)(blk - row * a.q8_0_nb);
         p = a.plane[0] + row * a.q8_0_nb * 32 + q8_0_row_offset(b, j, a.q8_0_nb);
     }
+    if (a.d_nb > 0 && plane == 1) {
+        int64_t row = blk / a.d_nb;
+        p = a.plane[1] + (row * CC_D_STRIDE(a.d_nb) + (blk - row * a.d_nb)) * 2 + j;
+    }
     if (TO_PLANES) *p = *g; else *g = *p;
 }
 
@@ -81,6 +87,7 @@ static RepackArgs make_args(const cc_buf* b) {
     a.n = ps.n;
     a.block_bytes = (int)cc_block_bytes(b->dtype);
     a.q8_0_nb = b->dtype == CC_Q8_0 ? (int)(b->cols / 32) : 0;
+    a.d_nb = CC_HAS_PADDED_D(b->dtype) ? (int)(b->cols / 32) : 0;
     for (int i = 0; i < CC_MAX_PLANES; i++) { a.plane[i] = b->plane[i]; a.bytes[i] = ps.bytes[i]; a.src_off[i] = ps.src_off[i]; }
     return a;
 }

@@ -57,7 +57,7 @@ struct TQ8_0 {
         // device layout: groups of 32 blocks, first halves then second halves (matvec_stream.cu)
         const int nb = k >> 5, nchunk = k >> 4;
         const int4* wq = (const int4*)W.p[0] + row * nchunk;
-        const uint16_t* wd = (const uint16_t*)W.p[1] + row * nb;
+        const uint16_t* wd = (const uint16_t*)W.p[1] + row * CC_D_STRIDE(nb);
         const int4* aq = (const int4*)sm;
         const float* ad = (const float*)(sm + al16i(k));
         float acc = 0.0f;
@@ -92,7 +92,7 @@ struct TQ4_0 {
     static __device__ float row_dot(const WPlanes& W, int64_t row, int k, const uint8_t* sm, int lane) {
         const int nb = k >> 5;
         const int4* wq = (const int4*)W.p[0] + row * nb;
-        const uint16_t* wd = (const uint16_t*)W.p[1] + row * nb;
+        const uint16_t* wd = (const uint16_t*)W.p[1] + row * CC_D_STRIDE(nb);
         const int4* aq = (const int4*)sm;
         const float* ad = (const float*)(sm + al16i(k));
         const int* as = (const int*)(sm + al16i(k) + al16i(nb * 4));
