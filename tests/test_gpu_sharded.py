@@ -83,12 +83,13 @@ def test_two_gpus_sharded_llama_matches_single_gpu():
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
 
 
-def test_two_processes_on_one_gpu_sharded_llama():
-    """World of 2 on ONE GPU, one process per rank (time-sliced contexts, peers' windows mapped through CUDA IPC exactly as across
+@pytest.mark.parametrize("n", [2, 8])
+def test_processes_on_one_gpu_sharded_llama(n):
+    """World of 2 / 8 on ONE GPU, one process per rank (time-sliced contexts, peers' windows mapped through CUDA IPC exactly as across
     GPUs): the exchange ops bit-exact against the rank-ordered numpy sum, and the 2-layer Llama-2-7B-shaped sharded model in the
     eager, CUDA-graph and megakernel modes -- ranks bit-identical, modes bit-identical, close to the unsharded logits.
-    This is the multi-GPU path's parity test on a single-GPU lease (tests/sharded_worker.py --one-gpu)."""
-    n = 2
+    This is the multi-GPU path's parity test on a single-GPU lease (tests/sharded_worker.py --one-gpu); world 8 runs the shard shapes
+    of the 8-GPU box (k = 512 / 1376: one short, ragged segment per row) through the same kernels."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "sharded_worker.py"), "--mode", "gpu", "--one-gpu"]
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
