@@ -230,10 +230,12 @@ def quick_decode(workload: str, local_rank: int, K: int, W: int, start_pos: int)
         for _ in range(W):
             tok = step_e2e(tok, pos); pos += 1
         dev.synchronize()
+        p0 = pos                                           # both timed regions decode at the same KV positions [p0, p0 + K)
         dev.timer_begin(); t0 = time.perf_counter()
         for _ in range(K):
             tok = step_e2e(tok, pos); pos += 1
         e2e_ms = max(dev.timer_end(), (time.perf_counter() - t0) * 1e3)
+        pos = p0
         l0 = dev.launch_count()
         dev.timer_begin()
         for i in range(K):
@@ -319,13 +321,14 @@ def run_b200(args, rank, world, local_rank):
     # device-side sampler that fed the next step.  No step waits for the host, so the GPU never idles between tokens.
     sampler = ClockSampler(local_rank); sampler.start()
     dev.synchronize(); barrier()
+    p0 = pos              # every timed region decodes K tokens at the SAME KV positions [p0, p0 + K): the regions differ in how the host is involved, not in context length
     launches0 = dev.launch_count()
     dev.timer_begin(); t0 = time.perf_counter()
     ids, lgs = runner.generate_greedy_logits([tok], K)
     host_ids = [int(np.flatnonzero(lg == lg.max())[-1]) for lg in lgs]
     e2e_ms_dev = dev.timer_end(); e2e_wall = time.perf_counter() - t0
     assert host_ids == ids and len(ids) == K, "host sampler and device sampler disagree"
-    pos += K; tok = ids[-1]
+    pos = p0; tok = ids[-1]
     launches_e2e = dev.launch_count() - launches0
     barrier()
     e2e_ms = max_over_ranks(max(e2e_ms_dev, e2e_wall * 1e3))      # host work (sampling) is part of e2e
@@ -335,6 +338,7 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(K):
         tok = step_e2e(tok, pos); pos += 1
     e2e_sync_ms = max_over_ranks(max(dev.timer_end(), (time.perf_counter() - t0) * 1e3))
+    pos = p0
     barrier()
     # ---- timed region 2: device-resident (no per-step host<->device traffic) -----------------------------------
     toks = [(tok * 31 + 7 * i) % conf.vocab_size for i in range(K)]
@@ -396,7 +400,7 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_step": val_ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}-decode-synthetic", "weights": wt_name, "classifier": ct_name, "kv_cache": "f32",
-                       "start_pos": args.start_pos, "mode": "lazy: plan not megakernel-eligible (matvec types outside Q8_0/Q4_0 use the warp-per-row kernels): fused kernels, CUDA-graph replay" if (lazy == 2 and launches_val != K) else {0: "eager (one launch per trait call)", 1: "lazy: fused kernels, CUDA-graph replay", 2: "lazy: one persistent megakernel per token, CUDA-graph replay"}[args.lazy],
+                       "start_pos": args.start_pos, "kv_positions": [int(p0), int(p0 + K)], "mode": "lazy: plan not megakernel-eligible (matvec types outside Q8_0/Q4_0 use the warp-per-row kernels): fused kernels, CUDA-graph replay" if (lazy == 2 and launches_val != K) else {0: "eager (one launch per trait call)", 1: "lazy: fused kernels, CUDA-graph replay", 2: "lazy: one persistent megakernel per token, CUDA-graph replay"}[args.lazy],
                        "multi_gpu": ("single GPU" if world == 1 else
                                      f"one token stream sharded over {world} GPUs: rows of wq/wk/wv/gate/up/classifier, block columns of wo/down; "
                                      f"exchange = {'one-shot NVLink peer stores fused into the megakernel' if transport == 'p2p' and lazy == 2 else 'one-shot NVLink peer-store kernel' if transport == 'p2p' else 'ncclAllReduce/ncclAllGather'} "

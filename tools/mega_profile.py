@@ -16,9 +16,10 @@ ct = capi.Q6_K if wl in ("Q4_K", "Q4_0-Q6K") else wt                            
 dev = CudaTensorDevice(0, lazy=2)
 conf = R.LLAMA2_7B
 w = R.synthetic_weights(dev, conf, wt, ct)
-r = R.LlamaRunner(dev, conf, w, 128)
+WARM = int(os.environ.get("MEGA_PROFILE_WARM", "40"))          # tokens decoded before the timed 40 (sets the KV length the profile sees)
+r = R.LlamaRunner(dev, conf, w, WARM + 88)
 pos = 0
-for i in range(40):
+for i in range(WARM):
     r.forward([1 + i], pos, export=False); pos += 1
 dev.synchronize()
 dev.timer_begin()
