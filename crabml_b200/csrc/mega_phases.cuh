@@ -665,6 +665,7 @@ static __device__ void phase_reduce(const MkPhase& ph, const CommDev& comm, unsi
                                // profiles/r02j: 2351 us vs 2265 us per token at N = 2)
 #define MK_F_TESTSTALL 128     // test hook: the last CTA leaves before barrier 2 -> every other CTA must time out, not hang
 #define MK_F_XEARLY 64         // the f32 row of the next fused prologue is requested (cp.async) right after the barrier opens
+#define MK_F_KVPF 2048         // ring kernel: the producer warps prefetch the attention phase's cached K / V rows into L2 one phase ahead
 #define MK_F_RPAIR 1024        // ring kernel: consumer warps take two units per round (shared activation loads; the slots are held twice as long)
 #define MK_F_RING 512          // weights through the TMA-fed shared-memory ring of mega_ring.cu (when every streaming phase qualifies)
 #define MK_F_EARLY 32          // a warp requests its first segments of the next MATVEC phase as soon as IT has finished its rows

@@ -102,7 +102,7 @@ __device__ __forceinline__ int mr_locate(const StreamMats& M, const MrGeo& g, in
 // cycles, so the number of polling warps bounds the refill rate, and at 8 the 80-register cap starts to cost.  Sleeping after a failed probe,
 // SIMT-wide parameter computation, in-order probe loops and fence-free hand-back words changed nothing.)
 __device__ void mr_producer(const MkPhase* __restrict__ phases, int n_phases, const MrRing R, unsigned full0, unsigned done0, unsigned ring0,
-                            MkPhase* s_pd, volatile unsigned* s_seq, volatile int* s_abort, int* s_prod_done, unsigned long long* prof_tail, const bool pairs) {
+                            MkPhase* s_pd, volatile unsigned* s_seq, volatile int* s_abort, int* s_prod_done, unsigned long long* prof_tail, const bool pairs, const bool kvpf, const uint8_t* __restrict__ dyn) {
     const int lane = threadIdx.x & 31;
     const int pt = (int)threadIdx.x - MK_THREADS;          // producer thread 0 .. 32 * MR_PRODUCER_WARPS - 1: owns the entries pt, pt + 128, ... of every phase
     unsigned long long p_trips = 0, p_cyc = 0, p_iss = 0;       // developer profiling (CTA 0 / lane 0)
@@ -115,6 +115,24 @@ __device__ void mr_producer(const MkPhase* __restrict__ phases, int n_phases, co
 #pragma unroll
         for (int j = 0; j < MR_DESC_PER_LANE; j++) { const int i = lane + 32 * j; nw[j] = (p + 1 < n_phases && i < MR_DESC_WORDS) ? ((const int*)(phases + p + 1))[i] : 0; }
         const MkPhase& ph = s_pd[p & 1];
+        if (kvpf && ph.type == MK_ATTN) {
+            // The attention phase streams a head's K and V rows through 48 KB of shared memory: latency x bytes in flight = 32 GB/s per head
+            // (profiles/r02y: +0.04 us per cached position and layer).  The producers reach this table entry while the compute warps are still in
+            // the qkv phase: they ask L2 for the cached rows [0, kv_len) of every kv head now, so that the phase's bulk copies hit L2.
+            // (rows written by earlier launches: stable; the current token's row never goes through the cache on its way to the phase)
+            const AttnArgs& a = ph.at;
+            const long long kv_len = ((const long long*)(dyn + ph.dyn_off))[1];
+            const unsigned ELT = a.kv_f16 ? 2u : 4u, PIECE = 4096u;
+            const size_t head_bytes = (size_t)kv_len * (size_t)a.hd * ELT;
+            const long long per_head = (long long)((head_bytes + PIECE - 1) / PIECE), per_cache = per_head * a.n_kv;
+            for (long long r = (long long)blockIdx.x * (32 * MR_PRODUCER_WARPS) + pt; r < 2 * per_cache; r += (long long)gridDim.x * (32 * MR_PRODUCER_WARPS)) {
+                const long long rr = r >= per_cache ? r - per_cache : r, gk = rr / per_head, piece = rr - gk * per_head;
+                const uint8_t* base = (const uint8_t*)(r >= per_cache ? a.vcache : a.kcache) + (size_t)gk * (size_t)a.seq_stride * ELT + (size_t)piece * PIECE;
+                const size_t left = head_bytes - (size_t)piece * PIECE;
+                const unsigned bytes = (unsigned)(left < PIECE ? left : PIECE) & ~15u;
+                if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"(bytes) : "memory");
+            }
+        }
         if (ph.type == MK_MATVEC && ph.act_type != CC_Q8_K) {
             const StreamArgs& A = ph.mv;
             const StreamMats& M = A.mats;
@@ -526,7 +544,7 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mega_ring_kernel(const MkPhase*
     __syncthreads();                         // the only barrier all 640 threads share
     if (threadIdx.x >= MK_THREADS) {
         mr_producer(phases, n_phases, R, full0, done0, (unsigned)__cvta_generic_to_shared(smem + R.ring_off), s_pd[(threadIdx.x - MK_THREADS) >> 5], s_seq, &s_abort, &s_prod_done,
-                    prof ? prof + (size_t)n_phases * MK_PROF_SLOTS : nullptr, (flags & MK_F_RPAIR) != 0);
+                    prof ? prof + (size_t)n_phases * MK_PROF_SLOTS : nullptr, (flags & MK_F_RPAIR) != 0, (flags & MK_F_KVPF) != 0, dyn);
         return;
     }
     MrCons RC;
