@@ -1,4 +1,8 @@
-// mega.cu -- one persistent kernel per token ("megakernel") for the fused decode path.
+// mega.cu -- one persistent kernel per token ("megakernel") for the fused decode path: the variant whose weight stream runs through
+// REGISTERS (two segments per warp in flight, look-ahead prefetch across the grid barrier).  Since round 2 the default is the variant in
+// mega_ring.cu (weights through a TMA-fed shared-memory ring: DESIGN.md section 4.5); this one is the fallback (CRABML_MEGA_FLAGS without
+// MK_F_RING, or a phase table whose working area leaves the ring fewer than 12 slots) and the A/B baseline.  The phase bodies both
+// kernels share live in mega_phases.cuh; the host side at the bottom of this file serves both.
 //
 // Why: profiles/r01c -- on B200 a kernel boundary costs ~4-5 us for a full-GPU streaming kernel (drain, launch latency,
 // ramp-up) and ~2-3 us for a tiny one; a fused Llama-2-7B token still has ~260 of them (~1 ms), as much as the 1.05 ms the
