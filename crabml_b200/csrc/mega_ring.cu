@@ -140,8 +140,8 @@ __device__ void mr_producer(const MkPhase* __restrict__ phases, int n_phases, co
             const unsigned BB = ph.wtype == CC_Q8_0 ? 32u : 16u;
             const unsigned doff = MK_SEG * 32u * BB;
             const int N = g.n_units * g.E, twoE = 2 * g.E, Npair = (g.n_units >> 1) * twoE;
-            // a flat loop, one probe of the lane's own slot per trip (mbarrier.test_wait: no suspension): lane l serves the entries l, l + 32, ...
-            // at its own pace, so a slot is refilled as soon as it is released, not when the slowest lane of a batch is ready
+            // a flat loop, one probe of the thread's own slot per trip (a load of the slot's "done" word: no suspension): thread t serves the entries
+            // t, t + 128, ... at its own pace, so a slot is refilled as soon as it is released, not when the slowest lane of a batch is ready
             int j = pt;
             bool have = false, mydead = false;
             const uint8_t* q0 = nullptr; const uint16_t* d0 = nullptr;
